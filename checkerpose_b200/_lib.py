@@ -1,0 +1,76 @@
+"""ctypes binding of libcheckerpose_b200.so (the C ABI declared in include/checkerpose_b200.h).
+
+The library is the product: if it is missing or fails to load, importing this module raises --
+there is no eager-PyTorch or CPU fallback behind any op.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+c_i32, c_i64, c_f32, c_vp, c_sz = C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+
+
+class ChainLayer(C.Structure):
+    _fields_ = [("w_packed", c_vp), ("bias", c_vp), ("kin", c_i32), ("nout", c_i32), ("act", c_i32), ("slope", c_f32)]
+
+
+class ChainParams(C.Structure):
+    _fields_ = [
+        ("prologue", c_i32), ("B", c_i32), ("N", c_i32),
+        ("src", c_vp), ("ld_src", c_i32), ("C", c_i32),
+        ("z", c_vp), ("ld_z", c_i32), ("Co", c_i32), ("idx", c_vp), ("graph_sel", c_vp), ("K", c_i32), ("agg_slope", c_f32),
+        ("patches", c_vp), ("Hp", c_i32), ("Wp", c_i32), ("E", c_i32), ("tap_step", c_i32),
+        ("x_id", c_vp), ("y_id", c_vp), ("mask", c_vp),
+        ("graph_feat", c_vp), ("ld_gf", c_i32), ("Cg", c_i32),
+        ("a_out", c_vp), ("ld_a_out", c_i32),
+        ("num_layers", c_i32),
+        ("layers", ChainLayer * 3),
+        ("out_mode", c_i32), ("out", c_vp), ("ld_out", c_i32), ("n_valid", c_i32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/checkerpose_b200.h
+SIGNATURES = {
+    "cp_last_error_string": (C.c_char_p, []),
+    "cp_version": (c_i32, []),
+    "cp_device_arch": (c_i32, []),
+    "cp_knn": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "cp_transpose_cn_to_nc": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cp_transpose_nc_to_cn": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cp_convert": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i64, c_vp]),
+    "cp_graph_feature": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cp_fold_edgeconv": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "cp_packed_weight_bytes": (c_sz, [c_i32, c_i32]),
+    "cp_pack_weight": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "cp_linear_f32": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_f32, c_vp, c_i32, c_i64, c_i32, c_vp]),
+    "cp_edge_aggregate": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_f32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cp_chain_fwd": (c_i32, [C.POINTER(ChainParams), c_vp]),
+    "cp_sample_taps": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "cp_decode_init": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "cp_decode_refine": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "cp_correspondences": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "cp_threshold": (c_i32, [c_vp, c_f32, c_i32, c_vp, c_i32, c_i64, c_vp]),
+    "cp_id_to_bits": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "cp_group_argmax": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]),
+    "cp_bits_to_id": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32, c_f32, c_i32, c_vp, c_i32, c_vp]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m checkerpose_b200.build` (or __graft_entry__.build()). "
+        "checkerpose_b200 has no fallback path.")
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)   # AttributeError here == the .so does not export a declared symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib.cp_last_error_string()
+        raise RuntimeError(f"checkerpose_b200 {what} failed ({status}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,45 @@
+// Shared host/device helpers for the checkerpose_b200 CUDA library.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/checkerpose_b200.h"
+
+namespace cp {
+
+void set_error(const char* fmt, ...);
+
+#define CP_REQUIRE(cond, code, ...)          \
+  do {                                        \
+    if (!(cond)) {                            \
+      cp::set_error(__VA_ARGS__);             \
+      return (code);                          \
+    }                                         \
+  } while (0)
+
+// Check the launch that was just issued.  cudaPeekAtLastError does not clear sticky state and is
+// legal during stream capture.
+#define CP_CHECK_LAUNCH(name)                                                      \
+  do {                                                                             \
+    cudaError_t e__ = cudaPeekAtLastError();                                       \
+    if (e__ != cudaSuccess) {                                                      \
+      cp::set_error("%s: CUDA error %d (%s)", name, (int)e__, cudaGetErrorString(e__)); \
+      (void)cudaGetLastError();                                                    \
+      return CP_E_CUDA;                                                            \
+    }                                                                              \
+  } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+}  // namespace cp

@@ -1,0 +1,400 @@
+"""Host-side orchestration of the GNN keypoint head on top of the C-ABI kernels.
+
+This is the engine shared by the drop-in modules in ``checkerpose_b200/model``: weight preparation
+(EdgeConv folding, bf16 tile packing, BN folding of the image branch) and the node-major forward of
+the init head, one refine stage and the whole progressive head.  Two compute modes:
+
+* ``torch.float32``  -- validation mode: FFMA GEMMs (``cp_linear_f32``), fp32 aggregation; matches the
+  reference to ~1e-5 and decodes bit-exactly outside the 1e-4 logit band.
+* ``torch.bfloat16`` -- product mode: the fused tcgen05 chain kernel (``cp_chain_fwd``), bf16 tensors in
+  HBM, fp32 accumulation in TMEM.
+
+The image branch (``up_net``, ``patch_generator``, ``seg_block``, ``conv1x1``) is dense convolution and
+stays on cuDNN/cuBLAS through torch, as SURVEY.md section 8 marks it (library part of the path).
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+_COMPUTE_DTYPE = torch.float32
+
+
+def set_compute_dtype(dtype) -> None:
+    """Select the arithmetic of the head: torch.float32 (validation) or torch.bfloat16 (product)."""
+    global _COMPUTE_DTYPE
+    if isinstance(dtype, str):
+        dtype = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16}[dtype]
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("compute dtype must be float32 or bfloat16")
+    _COMPUTE_DTYPE = dtype
+
+
+def get_compute_dtype():
+    return _COMPUTE_DTYPE
+
+
+@contextlib.contextmanager
+def _exact_fp32_convs(enabled: bool):
+    """fp32 validation mode must not silently run cuDNN convolutions in TF32."""
+    if not enabled:
+        yield
+        return
+    old_c, old_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_c, old_m
+
+
+# --------------------------------------------------------------------------------------------------
+# prepared weights (derived from the module parameters; never stored in the state_dict)
+# --------------------------------------------------------------------------------------------------
+class PreparedLinear:
+    def __init__(self, weight, bias, want_packed):
+        self.w = weight.detach().reshape(weight.shape[0], -1).contiguous().float()
+        self.b = None if bias is None else bias.detach().contiguous().float()
+        self.nout, self.kin = self.w.shape
+        self.packed = ops.pack_weight(self.w) if (want_packed and self.kin % 64 == 0) else None
+
+
+class PreparedEdgeConv(PreparedLinear):
+    """StaticGraph_module weights folded to the factored form [P|Q] (see cp_fold_edgeconv)."""
+
+    def __init__(self, sg_module, want_packed):
+        conv, bn, act = sg_module.conv[0], sg_module.conv[1], sg_module.conv[2]
+        wf, bf = ops.fold_edgeconv(conv.weight.detach(), bn.weight.detach(), bn.bias.detach(),
+                                   bn.running_mean.detach(), bn.running_var.detach(), bn.eps)
+        super().__init__(wf, bf, want_packed)
+        self.C, self.Co = wf.shape[1], wf.shape[0] // 2
+        self.slope = float(act.negative_slope)
+
+
+def _param_fingerprint(module: nn.Module):
+    return tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in list(module.parameters()) + list(module.buffers()))
+
+
+class PrepCache:
+    """Lazily (re)built prepared weights, invalidated when parameters change or move."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, owner: nn.Module, key, builder):
+        fp = (_param_fingerprint(owner), key)
+        hit = self._store.get(id(owner))
+        if hit is None or hit[0] != fp:
+            hit = (fp, builder())
+            self._store[id(owner)] = hit
+        return hit[1]
+
+
+_PREP = PrepCache()
+
+
+def prepared_edgeconv(sg_module, dtype) -> PreparedEdgeConv:
+    want = dtype == torch.bfloat16
+    return _PREP.get(sg_module, ("ec", want), lambda: PreparedEdgeConv(sg_module, want))
+
+
+def prepared_linear(lin: nn.Module, dtype) -> PreparedLinear:
+    want = dtype == torch.bfloat16
+    return _PREP.get(lin, ("lin", want), lambda: PreparedLinear(lin.weight, lin.bias, want))
+
+
+class GraphTable:
+    """int32 copy of a module's kNN index table: (G,N,K); G=1 for the single-object nets."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, knn_idx: torch.Tensor, device) -> torch.Tensor:
+        key = (knn_idx.data_ptr(), knn_idx._version, tuple(knn_idx.shape), str(device))
+        hit = cls._cache.get(key)
+        if hit is None:
+            hit = knn_idx.to(device=device, dtype=torch.int32).contiguous()
+            if len(cls._cache) > 256:
+                cls._cache.clear()
+            cls._cache[key] = hit
+        return hit
+
+
+def graph_select(knn_idx: torch.Tensor, obj_ids, batch: int, device):
+    """-> (idx32 (G,N,K), graph_sel int32 (B) or None).  LM nets index with 1-based ids (pipeline_lm.py:56-57)."""
+    if hasattr(knn_idx, "get"):       # LazyKnnGraph
+        knn_idx = knn_idx.get(device)
+    idx32 = GraphTable.get(knn_idx, device)
+    if obj_ids is not None:
+        return idx32, (obj_ids.to(device=device, dtype=torch.int64) - 1).to(torch.int32).contiguous()
+    if idx32.shape[0] == 1:
+        return idx32, None
+    if idx32.shape[0] != batch:
+        raise RuntimeError(f"knn_idx has {idx32.shape[0]} graphs for a batch of {batch}")
+    return idx32, torch.arange(batch, dtype=torch.int32, device=device)
+
+
+def _require_eval(module):
+    if module.training:
+        raise RuntimeError("checkerpose_b200 kernels fold BatchNorm running statistics and are inference-only: "
+                           "call .eval() (training-mode BN over B*N*K is out of scope)")
+
+
+def _chain_ok(C):
+    return C in (64, 128, 256)
+
+
+# --------------------------------------------------------------------------------------------------
+# EdgeConv (K2)
+# --------------------------------------------------------------------------------------------------
+def edgeconv_node_major(sg_module, x_nm, idx32, graph_sel, dtype):
+    """x_nm (B,N,C) of ``dtype`` -> (B,N,Co).  StaticGraph_module.forward (pipeline.py:55-59)."""
+    _require_eval(sg_module)
+    prep = prepared_edgeconv(sg_module, dtype)
+    B, N, C = x_nm.shape
+    if dtype == torch.float32:
+        z = ops.linear_f32(x_nm, prep.w, prep.b)
+        return ops.edge_aggregate(z, idx32, graph_sel, prep.slope)
+    if not (_chain_ok(C) and _chain_ok(prep.Co)):
+        raise RuntimeError(f"bf16 EdgeConv supports C, C' in {{64,128,256}} (got {C}->{prep.Co}); use float32 mode")
+    z = torch.empty((B, N, 2 * prep.Co), dtype=torch.bfloat16, device=x_nm.device)
+    ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x_nm,
+                  layers=[ops.chain_layer(prep.packed, prep.b, C, 2 * prep.Co, False, 0.0)], out=z, out_mode=ops.OUT_BF16)
+    return ops.edge_aggregate(z, idx32, graph_sel, prep.slope)
+
+
+# --------------------------------------------------------------------------------------------------
+# init head (InitNet_GNN.forward after the backbone, init.py:112-122)
+# --------------------------------------------------------------------------------------------------
+def init_head_node_major(init_net, feat_last, obj_ids, dtype):
+    """-> logits (B,N,7) f32, graph feature (B,N,64) of ``dtype``."""
+    _require_eval(init_net)
+    B = feat_last.shape[0]
+    N = init_net.npoint
+    dev = feat_last.device
+    with _exact_fp32_convs(dtype == torch.float32):
+        if dtype == torch.bfloat16:
+            conv = _bf16_module(init_net.conv1x1)
+            x0 = conv(feat_last.to(torch.bfloat16))
+        else:
+            x0 = init_net.conv1x1(feat_last.float())
+    x = x0.contiguous().view(B, N, 64)  # == out.view(-1, N, 64): channel = 8x8 cell (init.py:114)
+    blocks = list(init_net.pre_query_block)
+    idx32, sel = (None, None)
+    if blocks:
+        idx32, sel = graph_select(blocks[0]._knn, obj_ids, B, dev)
+    mlp = prepared_linear(init_net.mlp, dtype)
+    nbits = mlp.nout
+    if dtype == torch.float32:
+        for blk in blocks:
+            x = edgeconv_node_major(blk, x, idx32, sel, dtype)
+        logits = ops.linear_f32(x, mlp.w, mlp.b)
+        return logits, x
+    # bf16: LOAD->[Wcat_0] ; AGG->[Wcat_j] ... ; AGG(+store feature)->[mlp]
+    logits = torch.empty((B, N, 16), dtype=torch.float32, device=dev)
+    mlp_layer = ops.chain_layer(mlp.packed, mlp.b, 64, nbits, False, 0.0)
+    if not blocks:
+        ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x, layers=[mlp_layer], out=logits, out_mode=ops.OUT_F32, n_valid=nbits)
+        return logits, x
+    preps = [prepared_edgeconv(b, dtype) for b in blocks]
+    for b in blocks:
+        _require_eval(b)
+    z = torch.empty((B, N, 2 * preps[0].Co), dtype=torch.bfloat16, device=dev)
+    ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x,
+                  layers=[ops.chain_layer(preps[0].packed, preps[0].b, preps[0].C, 2 * preps[0].Co, False, 0.0)],
+                  out=z, out_mode=ops.OUT_BF16)
+    for j in range(1, len(blocks)):
+        z2 = torch.empty((B, N, 2 * preps[j].Co), dtype=torch.bfloat16, device=dev)
+        ops.chain_fwd(prologue=ops.PRO_AGG, B=B, N=N, z=z, idx32=idx32, graph_sel=sel, agg_slope=preps[j - 1].slope,
+                      layers=[ops.chain_layer(preps[j].packed, preps[j].b, preps[j].C, 2 * preps[j].Co, False, 0.0)],
+                      out=z2, out_mode=ops.OUT_BF16)
+        z = z2
+    gfeat = torch.empty((B, N, preps[-1].Co), dtype=torch.bfloat16, device=dev)
+    ops.chain_fwd(prologue=ops.PRO_AGG, B=B, N=N, z=z, idx32=idx32, graph_sel=sel, agg_slope=preps[-1].slope, a_out=gfeat,
+                  layers=[mlp_layer], out=logits, out_mode=ops.OUT_F32, n_valid=nbits)
+    return logits, gfeat
+
+
+# --------------------------------------------------------------------------------------------------
+# image branch helpers (library convolutions)
+# --------------------------------------------------------------------------------------------------
+class _FoldedSeq:
+    """bf16, channels_last, BN-folded functional copy of a conv stack (up_net block / single conv)."""
+
+    def __init__(self, module):
+        mods = list(module) if isinstance(module, nn.Sequential) else [module]
+        self.ops = []
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                w = m.weight.detach().float()
+                b = None if m.bias is None else m.bias.detach().float()
+                if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d):
+                    bn = mods[i + 1]
+                    sc = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+                    sh = bn.bias.detach().float() - sc * bn.running_mean.detach().float()
+                    if isinstance(m, nn.ConvTranspose2d):
+                        w = w * sc.view(1, -1, 1, 1)
+                    else:
+                        w = w * sc.view(-1, 1, 1, 1)
+                    b = sh if b is None else b * sc + sh
+                    i += 1
+                kind = "convT" if isinstance(m, nn.ConvTranspose2d) else "conv"
+                self.ops.append((kind, w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
+                                 None if b is None else b.to(torch.bfloat16), m))
+            elif isinstance(m, nn.ReLU):
+                self.ops.append(("relu", None, None, m))
+            elif isinstance(m, nn.LeakyReLU):
+                self.ops.append(("lrelu", None, None, m))
+            elif isinstance(m, nn.UpsamplingBilinear2d):
+                self.ops.append(("up", None, None, m))
+            else:
+                raise RuntimeError(f"unsupported layer in image branch: {type(m).__name__}")
+            i += 1
+
+    def __call__(self, x):
+        x = x.contiguous(memory_format=torch.channels_last)
+        for kind, w, b, m in self.ops:
+            if kind == "conv":
+                x = F.conv2d(x, w, b, stride=m.stride, padding=m.padding)
+            elif kind == "convT":
+                x = F.conv_transpose2d(x, w, b, stride=m.stride, padding=m.padding, output_padding=m.output_padding)
+            elif kind == "relu":
+                x = torch.relu_(x)
+            elif kind == "lrelu":
+                x = F.leaky_relu(x, m.negative_slope)
+            else:
+                x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        return x
+
+
+def _bf16_module(module):
+    _require_eval(module)
+    return _PREP.get(module, ("bf16seq",), lambda: _FoldedSeq(module))
+
+
+def image_block(module, x, dtype):
+    """Run an image-branch block (up_net[i], patch_generator, seg_block) in ``dtype`` on cuDNN."""
+    with _exact_fp32_convs(dtype == torch.float32):
+        if dtype == torch.bfloat16:
+            return _bf16_module(module)(x.to(torch.bfloat16))
+        return module(x.float())
+
+
+def patches_nhwc(patch_generator, img_feat, dtype):
+    p = image_block(patch_generator, img_feat, dtype)  # (B,E,Hp,Wp)
+    return p.permute(0, 2, 3, 1).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# refine stage (Refine_moduleGNN.forward, pipeline.py:262-298)
+# --------------------------------------------------------------------------------------------------
+def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, obj_ids, dtype):
+    """gfeat_nm (B,N,Cg) of ``dtype``, roi_mask (B,N) f32 {0,1}, ids (B,N) int64.
+    -> logits (B,N,>=2) f32 [x_new, y_new], graph feature (B,N,C) of ``dtype``."""
+    _require_eval(ref)
+    B, N, Cg = gfeat_nm.shape
+    dev = gfeat_nm.device
+    k = ref.local_feat_ext_block.kernel_size
+    patches = patches_nhwc(ref.local_feat_ext_block.patch_generator, img_feat, dtype)
+    pg0 = prepared_linear(ref.pre_graph_module[0], dtype)
+    pg1 = prepared_linear(ref.pre_graph_module[2], dtype)
+    slope = float(ref.pre_graph_module[1].negative_slope)
+    blocks = list(ref.pre_query_block)
+    q = [prepared_linear(ref.query_block.mlps[i], dtype) for i in (0, 2, 4)]
+    qslope = float(ref.query_block.mlps[1].negative_slope)
+    idx32, sel = (None, None)
+    if blocks:
+        idx32, sel = graph_select(blocks[0]._knn, obj_ids, B, dev)
+    x_id = x_id.contiguous()
+    y_id = y_id.contiguous()
+    if dtype == torch.float32:
+        taps = ops.sample_taps(patches, x_id, y_id, roi_mask, k)
+        h = ops.linear_f32(taps, pg0.w, pg0.b, True, slope, a2=gfeat_nm)
+        h = ops.linear_f32(h, pg1.w, pg1.b, True, slope)
+        for blk in blocks:
+            h = edgeconv_node_major(blk, h, idx32, sel, dtype)
+        t = ops.linear_f32(h, q[0].w, q[0].b, True, qslope)
+        t = ops.linear_f32(t, q[1].w, q[1].b, True, qslope)
+        logits = ops.linear_f32(t, q[2].w, q[2].b)
+        return logits, h
+    # ---- bf16 fused chains ----
+    E = patches.shape[-1]
+    if not (E == 64 and _chain_ok(Cg) and pg0.nout == 256 and pg1.nout == 256 and q[0].kin == 256):
+        raise RuntimeError("bf16 refine stage supports the shipped dims (num_filters=256, query_dims=(256,256,64)); "
+                           "use float32 mode for other shapes")
+    preps = [prepared_edgeconv(b, dtype) for b in blocks]
+    for b in blocks:
+        _require_eval(b)
+    pg_layers = [ops.chain_layer(pg0.packed, pg0.b, pg0.kin, pg0.nout, True, slope),
+                 ops.chain_layer(pg1.packed, pg1.b, pg1.kin, pg1.nout, True, slope)]
+    q_layers = [ops.chain_layer(q[0].packed, q[0].b, q[0].kin, q[0].nout, True, qslope),
+                ops.chain_layer(q[1].packed, q[1].b, q[1].kin, q[1].nout, True, qslope),
+                ops.chain_layer(q[2].packed, q[2].b, q[2].kin, q[2].nout, False, 0.0)]
+    logits = torch.empty((B, N, 16), dtype=torch.float32, device=dev)
+    common = dict(B=B, N=N)
+    taps_args = dict(prologue=ops.PRO_TAPS, patches=patches, tap_step=k, x_id=x_id, y_id=y_id, mask=roi_mask,
+                     graph_feat=gfeat_nm)
+    if not blocks:
+        feat = torch.empty((B, N, 256), dtype=torch.bfloat16, device=dev)
+        ops.chain_fwd(**common, **taps_args, layers=pg_layers, out=feat, out_mode=ops.OUT_BF16)
+        ops.chain_fwd(**common, prologue=ops.PRO_LOAD, src=feat, layers=q_layers, out=logits, out_mode=ops.OUT_F32,
+                      n_valid=q[2].nout)
+        return logits, feat
+    z = torch.empty((B, N, 2 * preps[0].Co), dtype=torch.bfloat16, device=dev)
+    ops.chain_fwd(**common, **taps_args,
+                  layers=pg_layers + [ops.chain_layer(preps[0].packed, preps[0].b, preps[0].C, 2 * preps[0].Co, False, 0.0)],
+                  out=z, out_mode=ops.OUT_BF16)
+    for j in range(1, len(blocks)):
+        z2 = torch.empty_like(z)
+        ops.chain_fwd(**common, prologue=ops.PRO_AGG, z=z, idx32=idx32, graph_sel=sel, agg_slope=preps[j - 1].slope,
+                      layers=[ops.chain_layer(preps[j].packed, preps[j].b, preps[j].C, 2 * preps[j].Co, False, 0.0)],
+                      out=z2, out_mode=ops.OUT_BF16)
+        z = z2
+    feat = torch.empty((B, N, preps[-1].Co), dtype=torch.bfloat16, device=dev)
+    ops.chain_fwd(**common, prologue=ops.PRO_AGG, z=z, idx32=idx32, graph_sel=sel, agg_slope=preps[-1].slope, a_out=feat,
+                  layers=q_layers, out=logits, out_mode=ops.OUT_F32, n_valid=q[2].nout)
+    return logits, feat
+
+
+# --------------------------------------------------------------------------------------------------
+# whole progressive head (PoseNet_GNNskip.forward after the backbone, pipeline.py:351-384)
+# --------------------------------------------------------------------------------------------------
+def pose_head_forward(net, img_feats, obj_ids=None, stage=None, dtype=None, bbox=None):
+    """-> (roi_bit (B,1,N), x_bits (B,L,N), y_bits (B,L,N), seg (B,2,H,W), x_id (B,N), y_id (B,N)) as the reference,
+    plus correspondence records (B,N,3) int32 when ``bbox`` (B,4) is given (else None)."""
+    dtype = dtype or get_compute_dtype()
+    _require_eval(net)
+    nact = net.num_refine_steps if stage is None else stage
+    feat_last = img_feats[-1]
+    B, dev, N = feat_last.shape[0], feat_last.device, net.npoint
+    logits0, gfeat = init_head_node_major(net.init_net, feat_last, obj_ids, dtype)
+    L0 = (net.init_net.num_out_bits - 1) // 2
+    Ltot = L0 + nact
+    roi_bit = torch.empty((B, 1, N), dtype=torch.float32, device=dev)
+    x_bits = torch.empty((B, Ltot, N), dtype=torch.float32, device=dev)
+    y_bits = torch.empty((B, Ltot, N), dtype=torch.float32, device=dev)
+    roi_mask = torch.empty((B, N), dtype=torch.float32, device=dev)
+    x_id = torch.empty((B, N), dtype=torch.int64, device=dev)
+    y_id = torch.empty((B, N), dtype=torch.int64, device=dev)
+    ops.decode_init(logits0, L0, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id)
+    img_feat = feat_last
+    for i in range(nact):
+        if i > 0:
+            skip = img_feats[-i - 1]
+            img_feat = torch.cat([img_feat, skip.to(img_feat.dtype)], dim=1)
+        img_feat = image_block(net.up_net[i], img_feat, dtype)
+        logits, gfeat = refine_node_major(net.refine_net[i], img_feat, gfeat, roi_mask, x_id, y_id, obj_ids, dtype)
+        ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id)
+    seg = image_block(net.seg_block, img_feat, dtype).float().contiguous()
+    corr = None
+    if bbox is not None:
+        corr = ops.correspondences(roi_bit, seg, bbox, x_id, y_id)
+    return (roi_bit, x_bits, y_bits, seg, x_id, y_id), corr

@@ -1,0 +1,337 @@
+"""Tensor-level wrappers over the C ABI (include/checkerpose_b200.h).
+
+PyTorch is used for device memory (``torch.empty``) and the current CUDA stream only; every
+computation below is one or more launches of the hand-written kernels in ``csrc/``.  Inputs must be
+CUDA tensors: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ChainLayer, ChainParams, check, lib
+
+CP_F32, CP_BF16 = 0, 1
+PRO_LOAD, PRO_AGG, PRO_TAPS = 0, 1, 2
+OUT_BF16, OUT_F32 = 0, 1
+
+#: number of kernel launches issued through this module (bench.py reports it as ``gpu_launches``)
+launch_count = 0
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("checkerpose_b200: expected a CUDA tensor (there is no CPU fallback); got device "
+                               f"{t.device}")
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return CP_F32
+    if t.dtype == torch.bfloat16:
+        return CP_BF16
+    raise RuntimeError(f"checkerpose_b200: unsupported dtype {t.dtype}")
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def knn(x: torch.Tensor, k: int, want_i32: bool = False):
+    """x (B,C,N) float32 -> idx (B,N,k) int64 [, int32 copy].  pipeline.py:18-23."""
+    _need_cuda(x)
+    if x.dim() != 3:
+        raise RuntimeError("knn: x must be (B, C, N)")
+    x = x.contiguous().float()
+    B, Cc, N = x.shape
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+    idx32 = torch.empty((B, N, k), dtype=torch.int32, device=x.device) if want_i32 else None
+    check(lib.cp_knn(_p(x), B, Cc, N, int(k), _p(idx), _p(idx32), _stream()), "cp_knn")
+    _count()
+    return (idx, idx32) if want_i32 else idx
+
+
+# --------------------------------------------------------------------------------------- layout
+def is_node_major_view(x: torch.Tensor) -> bool:
+    """True if the (B,C,N) tensor is a permuted view of contiguous (B,N,C) storage."""
+    return x.dim() == 3 and x.permute(0, 2, 1).is_contiguous()
+
+
+def to_node_major(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """(B,C,N) -> contiguous (B,N,C) of ``dtype``; zero-copy when x already is such a view."""
+    _need_cuda(x)
+    B, Cc, N = x.shape
+    if is_node_major_view(x):
+        v = x.permute(0, 2, 1)
+        if v.dtype == dtype:
+            return v
+        out = torch.empty((B, N, Cc), dtype=dtype, device=x.device)
+        check(lib.cp_convert(_p(v), _dt(v), _p(out), _dt(out), v.numel(), _stream()), "cp_convert")
+        _count()
+        return out
+    x = x.contiguous()
+    out = torch.empty((B, N, Cc), dtype=dtype, device=x.device)
+    check(lib.cp_transpose_cn_to_nc(_p(x), _dt(x), _p(out), _dt(out), B, Cc, N, _stream()), "cp_transpose_cn_to_nc")
+    _count()
+    return out
+
+
+def to_channel_major(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """contiguous (B,N,C) -> contiguous (B,C,N) of ``dtype``."""
+    _need_cuda(x)
+    x = x.contiguous()
+    B, N, Cc = x.shape
+    out = torch.empty((B, Cc, N), dtype=dtype, device=x.device)
+    check(lib.cp_transpose_nc_to_cn(_p(x), _dt(x), _p(out), _dt(out), B, N, Cc, _stream()), "cp_transpose_nc_to_cn")
+    _count()
+    return out
+
+
+def convert(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype == dtype:
+        return x
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(lib.cp_convert(_p(x), _dt(x), _p(out), _dt(out), x.numel(), _stream()), "cp_convert")
+    _count()
+    return out
+
+
+def graph_feature(x: torch.Tensor, idx32: torch.Tensor, graph_sel=None) -> torch.Tensor:
+    """get_graph_feature (pipeline.py:27-40): x (B,C,N) f32 -> (B,2C,N,K) f32."""
+    _need_cuda(x, idx32, graph_sel)
+    x = x.contiguous().float()
+    B, Cc, N = x.shape
+    K = idx32.shape[-1]
+    out = torch.empty((B, 2 * Cc, N, K), dtype=torch.float32, device=x.device)
+    check(lib.cp_graph_feature(_p(x), _p(idx32), _p(graph_sel), _p(out), B, Cc, N, K, _stream()), "cp_graph_feature")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------- weight preparation
+def fold_edgeconv(conv_w, gamma, beta, mean, var, eps=1e-5):
+    """-> (w_fold (2Co,C) f32, b_fold (2Co) f32); see cp_fold_edgeconv in the header for the algebra."""
+    _need_cuda(conv_w, gamma, beta, mean, var)
+    Co, C2 = conv_w.shape[0], conv_w.shape[1]
+    Cc = C2 // 2
+    w = conv_w.reshape(Co, C2).contiguous().float()
+    wf = torch.empty((2 * Co, Cc), dtype=torch.float32, device=w.device)
+    bf = torch.empty((2 * Co,), dtype=torch.float32, device=w.device)
+    check(lib.cp_fold_edgeconv(_p(w), _p(gamma.contiguous().float()), _p(beta.contiguous().float()),
+                               _p(mean.contiguous().float()), _p(var.contiguous().float()), float(eps), Cc, Co,
+                               _p(wf), _p(bf), _stream()), "cp_fold_edgeconv")
+    _count()
+    return wf, bf
+
+
+def pack_weight(w: torch.Tensor) -> torch.Tensor:
+    """(Nout,K) f32 -> packed bf16 tile image (uint8 tensor) for the tcgen05 chain kernel."""
+    _need_cuda(w)
+    w = w.contiguous().float()
+    Nout, K = w.shape
+    nbytes = lib.cp_packed_weight_bytes(Nout, K)
+    if nbytes == 0:
+        raise RuntimeError(f"pack_weight: unsupported shape ({Nout},{K}); K must be a multiple of 64")
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+    check(lib.cp_pack_weight(_p(w), Nout, K, _p(out), _stream()), "cp_pack_weight")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------ fp32 path
+def linear_f32(a1, w, bias=None, act=False, slope=0.0, a2=None, out=None):
+    """y = act([a1|a2] @ w.T + bias); a* are (..., K*) row-major views with unit inner stride."""
+    _need_cuda(a1, w, bias, a2)
+    K1 = a1.shape[-1]
+    M = a1.numel() // K1
+    K2 = 0 if a2 is None else a2.shape[-1]
+    Nout = w.shape[0]
+    assert w.shape[1] == K1 + K2 and a1.stride(-1) == 1
+    a1 = a1 if a1.is_contiguous() else a1.contiguous()
+    if a2 is not None:
+        a2 = a2 if a2.is_contiguous() else a2.contiguous()
+    if out is None:
+        out = torch.empty(a1.shape[:-1] + (Nout,), dtype=torch.float32, device=a1.device)
+    check(lib.cp_linear_f32(_p(a1), K1, K1, _p(a2), K2, K2, _p(w), _p(bias), int(bool(act)), float(slope), _p(out),
+                            out.stride(-2) if out.dim() > 1 else Nout, M, Nout, _stream()), "cp_linear_f32")
+    _count()
+    return out
+
+
+def edge_aggregate(z, idx32, graph_sel, slope, out=None):
+    """z (B,N,2Co) -> y (B,N,Co):  lrelu(max_k z[b,idx[i,k],:Co] + z[b,i,Co:])."""
+    _need_cuda(z, idx32, graph_sel)
+    B, N, C2 = z.shape
+    Co = C2 // 2
+    K = idx32.shape[-1]
+    assert z.is_contiguous() and idx32.is_contiguous() and idx32.shape[-2] == N
+    if out is None:
+        out = torch.empty((B, N, Co), dtype=z.dtype, device=z.device)
+    check(lib.cp_edge_aggregate(_p(z), _dt(z), _p(idx32), _p(graph_sel), float(slope), _p(out), B, N, K, Co, _stream()),
+          "cp_edge_aggregate")
+    _count()
+    return out
+
+
+def sample_taps(patches_nhwc, x_id, y_id, mask, tap_step, out=None):
+    """patches (B,Hp,Wp,E) contiguous, ids (B,N) int64, mask (B,N) f32|None -> (B,N,4E)."""
+    _need_cuda(patches_nhwc, x_id, y_id, mask)
+    B, Hp, Wp, E = patches_nhwc.shape
+    N = x_id.shape[1]
+    assert patches_nhwc.is_contiguous() and x_id.is_contiguous() and y_id.is_contiguous()
+    assert x_id.dtype == torch.int64 and y_id.dtype == torch.int64
+    if out is None:
+        out = torch.empty((B, N, 4 * E), dtype=patches_nhwc.dtype, device=patches_nhwc.device)
+    check(lib.cp_sample_taps(_p(patches_nhwc), _dt(patches_nhwc), Hp, Wp, E, int(tap_step), _p(x_id), _p(y_id), _p(mask),
+                             _p(out), B, N, _stream()), "cp_sample_taps")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------- tcgen05 chain
+def chain_layer(w_packed, bias, kin, nout, act, slope) -> ChainLayer:
+    return ChainLayer(C.c_void_p(w_packed.data_ptr()), _p(bias), int(kin), int(nout), int(bool(act)), float(slope))
+
+
+def chain_fwd(*, prologue, B, N, layers, out, out_mode, n_valid=0,
+              src=None, z=None, idx32=None, graph_sel=None, agg_slope=0.2, a_out=None,
+              patches=None, tap_step=2, x_id=None, y_id=None, mask=None, graph_feat=None):
+    """One launch of the fused tcgen05 chain (see cp_chain_fwd in the header).  All tensors bf16
+    node-major unless noted; ``out`` is (B,N,ld) bf16 (OUT_BF16) or f32 (OUT_F32)."""
+    _need_cuda(out, src, z, idx32, graph_sel, a_out, patches, x_id, y_id, mask, graph_feat)
+    p = ChainParams()
+    p.prologue, p.B, p.N = prologue, B, N
+    if prologue == PRO_LOAD:
+        assert src.dtype == torch.bfloat16 and src.stride(-1) == 1
+        p.src, p.ld_src, p.C = _p(src), src.stride(-2), src.shape[-1]
+    elif prologue == PRO_AGG:
+        assert z.dtype == torch.bfloat16 and z.is_contiguous() and idx32.dtype == torch.int32 and idx32.is_contiguous()
+        p.z, p.ld_z, p.Co = _p(z), z.shape[-1], z.shape[-1] // 2
+        p.idx, p.graph_sel, p.K, p.agg_slope = _p(idx32), _p(graph_sel), idx32.shape[-1], float(agg_slope)
+        if a_out is not None:
+            assert a_out.dtype == torch.bfloat16 and a_out.is_contiguous()
+            p.a_out, p.ld_a_out = _p(a_out), a_out.shape[-1]
+    elif prologue == PRO_TAPS:
+        assert patches.dtype == torch.bfloat16 and patches.is_contiguous() and graph_feat.dtype == torch.bfloat16
+        assert x_id.dtype == torch.int64 and y_id.dtype == torch.int64 and graph_feat.is_contiguous()
+        p.patches, p.Hp, p.Wp, p.E, p.tap_step = _p(patches), patches.shape[1], patches.shape[2], patches.shape[3], int(tap_step)
+        p.x_id, p.y_id, p.mask = _p(x_id), _p(y_id), _p(mask)
+        p.graph_feat, p.ld_gf, p.Cg = _p(graph_feat), graph_feat.shape[-1], graph_feat.shape[-1]
+    else:
+        raise RuntimeError("chain_fwd: bad prologue")
+    p.num_layers = len(layers)
+    for i, L in enumerate(layers):
+        p.layers[i] = L
+    p.out_mode, p.out, p.ld_out, p.n_valid = out_mode, _p(out), out.shape[-1], int(n_valid)
+    check(lib.cp_chain_fwd(C.byref(p), _stream()), "cp_chain_fwd")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------- K4 decode
+def decode_init(logits, L, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id):
+    _need_cuda(logits, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id)
+    B, N = x_id.shape
+    check(lib.cp_decode_init(_p(logits), logits.shape[-1], L, Ltot, _p(roi_bit), _p(x_bits), _p(y_bits), _p(roi_mask),
+                             _p(x_id), _p(y_id), B, N, _stream()), "cp_decode_init")
+    _count()
+
+
+def decode_refine(logits, plane, Ltot, x_bits, y_bits, x_id, y_id):
+    _need_cuda(logits, x_bits, y_bits, x_id, y_id)
+    B, N = x_id.shape
+    check(lib.cp_decode_refine(_p(logits), logits.shape[-1], plane, Ltot, _p(x_bits), _p(y_bits), _p(x_id), _p(y_id), B, N,
+                               _stream()), "cp_decode_refine")
+    _count()
+
+
+CORR_DTYPE_BYTES = 12
+
+
+def correspondences(roi_bit, seg, bbox, x_id, y_id, out=None):
+    """-> (B,N,3) int32 view of records {f32 u, f32 v, u32 flags}; see cp_correspondences."""
+    _need_cuda(roi_bit, seg, bbox, x_id, y_id)
+    B, N = x_id.shape
+    S = seg.shape[-1]
+    assert seg.shape[1] == 2 and seg.is_contiguous() and roi_bit.is_contiguous() and bbox.shape == (B, 4)
+    if out is None:
+        out = torch.empty((B, N, 3), dtype=torch.int32, device=x_id.device)
+    check(lib.cp_correspondences(_p(roi_bit), _p(seg.float()), _p(bbox.contiguous().float()), _p(x_id), _p(y_id), _p(out),
+                                 B, N, S, _stream()), "cp_correspondences")
+    _count()
+    return out
+
+
+def split_correspondences(rec: torch.Tensor):
+    """(…,3) int32 records -> (uv float32 (…,2), flags int32 (…))."""
+    uv = rec[..., :2].contiguous().view(torch.float32)
+    return uv, rec[..., 2]
+
+
+def threshold(x, thr=0.5, apply_sigmoid=True, as_long=False):
+    _need_cuda(x)
+    x = x.contiguous().float()
+    out = torch.empty(x.shape, dtype=torch.int64 if as_long else torch.float32, device=x.device)
+    check(lib.cp_threshold(_p(x), float(thr), int(apply_sigmoid), _p(out), int(as_long), x.numel(), _stream()), "cp_threshold")
+    _count()
+    return out
+
+
+def bits_to_id(x, code_dim, binarize, thr=0.5, base=2, as_long=True):
+    """Reduce dimension ``code_dim`` of x (MSB first) to an id; output has that dimension removed."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    shape = list(x.shape)
+    L = shape[code_dim]
+    outer = 1
+    for s in shape[:code_dim]:
+        outer *= s
+    inner = 1
+    for s in shape[code_dim + 1:]:
+        inner *= s
+    out_shape = shape[:code_dim] + shape[code_dim + 1:]
+    out = torch.empty(out_shape, dtype=torch.int64 if as_long else torch.float32, device=x.device)
+    check(lib.cp_bits_to_id(_p(x), outer, L, inner, L * inner, inner, 1, int(binarize), float(thr), int(base), _p(out),
+                            int(as_long), _stream()), "cp_bits_to_id")
+    _count()
+    return out
+
+
+def id_to_bits(ids, L, base=2):
+    """ids (...,) int64 -> (..., L) f32 digits, MSB first (class_id_encoder_decoder.py:88-101)."""
+    _need_cuda(ids)
+    ids = ids.contiguous().to(torch.int64)
+    out = torch.empty(tuple(ids.shape) + (int(L),), dtype=torch.float32, device=ids.device)
+    check(lib.cp_id_to_bits(_p(ids), ids.numel(), int(L), int(base), _p(out), _stream()), "cp_id_to_bits")
+    _count()
+    return out
+
+
+def group_argmax(x, D):
+    """x (G*D, H, W)-like viewed as (G, D, inner) -> (G, inner) int64 argmax over D."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    total = x.numel()
+    inner = 1
+    for s in x.shape[2:]:
+        inner *= s
+    G = total // (D * inner)
+    out = torch.empty((G, inner), dtype=torch.int64, device=x.device)
+    check(lib.cp_group_argmax(_p(x), G, int(D), inner, _p(out), _stream()), "cp_group_argmax")
+    _count()
+    return out

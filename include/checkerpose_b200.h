@@ -1,0 +1,177 @@
+/*
+ * checkerpose_b200 -- C ABI of the B200 (sm_100a) kernels behind CheckerPose's GNN keypoint head.
+ *
+ * The reference (RuyiLian/CheckerPose) has no native code and no FFI: the "operator interface" of
+ * this path is the Python nn.Module / function API of checkerpose/model/{init,init_lm,pipeline,
+ * pipeline_lm}.py.  Each entry point below names the reference function(s) it replaces; the
+ * Python drop-in modules in checkerpose_b200/model/ bind them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all buffers
+ *     (inputs, outputs, packed weights); the library never allocates or frees device memory;
+ *   - every launch goes to the cudaStream_t passed in (an opaque void* here), is asynchronous and
+ *     CUDA-graph capturable; no internal synchronisation, no mutable global state;
+ *   - "node-major" = (B, N, C) row-major with C contiguous.  The reference's (B, C, N) tensors are
+ *     converted at the module boundary (cp_transpose_*), or are zero-copy permuted views;
+ *   - return value: 0 on success, negative on error (CP_E_*); cp_last_error_string() gives the
+ *     message for the calling thread.  Nothing throws or aborts across the ABI;
+ *   - there is no CPU fallback anywhere.
+ */
+#ifndef CHECKERPOSE_B200_H_
+#define CHECKERPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cp_stream_t; /* cudaStream_t */
+
+enum { CP_F32 = 0, CP_BF16 = 1 };
+enum {
+  CP_OK = 0,
+  CP_E_INVALID = -1,     /* bad argument / null pointer / misaligned */
+  CP_E_UNSUPPORTED = -2, /* shape outside what the kernel handles */
+  CP_E_CUDA = -3         /* CUDA runtime error captured at launch */
+};
+
+const char* cp_last_error_string(void);
+int cp_version(void);
+/* Compute capability of the current device as major*10+minor (100 on B200), or <0 on error. */
+int cp_device_arch(void);
+
+/* ---- K1: kNN graph -------------------------------------------------------------------------
+ * knn(x, k)  pipeline.py:18-23 == init.py:27-32 == pipeline_lm.py:18-23 == init_lm.py:27-32.
+ * x (B, C, N) f32 -> idx64 (B, N, k) int64, nearest first (self is entry 0); optional int32 copy
+ * idx32 (may be NULL).  fp32 direct-difference distances, ties broken towards the lower index.
+ * 1 <= k <= 64, k <= N, C <= 64. */
+int cp_knn(const float* x, int B, int C, int N, int k, int64_t* idx64, int32_t* idx32, cp_stream_t s);
+
+/* ---- layout conversion at the module boundary ----------------------------------------------
+ * (B, C, N) <-> (B, N, C), with dtype conversion (CP_F32 / CP_BF16 on either side). */
+int cp_transpose_cn_to_nc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C, int N, cp_stream_t s);
+int cp_transpose_nc_to_cn(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int N, int C, cp_stream_t s);
+int cp_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, cp_stream_t s);
+
+/* ---- get_graph_feature(x, knn_idx, batch_indices)  pipeline.py:27-40 ------------------------
+ * Kept for API completeness (the fused path never materialises it).
+ * x (B, C, N) f32, idx (G, N, K) int32, graph_sel (B) int32 or NULL (=> graph 0) -> out (B, 2C, N, K). */
+int cp_graph_feature(const float* x, const int32_t* idx, const int32_t* graph_sel, float* out,
+                     int B, int C, int N, int K, cp_stream_t s);
+
+/* ---- weight preparation (module-owned, derived lazily after load_state_dict) ----------------
+ * EdgeConv folding: StaticGraph_module = Conv2d(2C->Co,1x1,no bias)+BatchNorm2d(eval)+LeakyReLU+max_k
+ * (pipeline.py:45-59).  With W=[W1|W2], s=gamma/sqrt(var+eps), t=beta-s*mean:
+ *   max_k lrelu(s*(W1(x_j-x_i)+W2 x_i)+t) = lrelu(max_k P_j + Q_i),  P=(s.W1)x, Q=(s.(W2-W1))x+t
+ * (max commutes because lrelu is increasing; folding s into the rows removes the sign problem of
+ * negative gammas).  w_fold (2Co, C) f32 = [s.W1 ; s.(W2-W1)], b_fold (2Co) = [0 ; t]. */
+int cp_fold_edgeconv(const float* conv_w, const float* gamma, const float* beta, const float* mean,
+                     const float* var, float eps, int C, int Co, float* w_fold, float* b_fold, cp_stream_t s);
+/* Pack an (Nout, K) f32 row-major weight into the bf16 tile image the tcgen05 kernels stream with
+ * bulk copies: N blocks of <=128 rows (Nout padded to 16), K chunks of 64, each tile K-major
+ * SWIZZLE_128B.  K % 64 == 0. */
+size_t cp_packed_weight_bytes(int Nout, int K);
+int cp_pack_weight(const float* w, int Nout, int K, void* packed, cp_stream_t s);
+
+/* ---- fp32 validation path (SIMT FFMA) -------------------------------------------------------
+ * y[m, :] = act([a1[m, :K1] | a2[m, :K2]] . w^T + bias);  w (Nout, K1+K2) row-major;  a2 may be NULL.
+ * act: 0 = none, 1 = LeakyReLU(slope).  Replaces nn.Linear(+LeakyReLU) (pipeline.py:61-69) and the
+ * folded EdgeConv node GEMM. */
+int cp_linear_f32(const float* a1, int lda1, int K1, const float* a2, int lda2, int K2, const float* w,
+                  const float* bias, int act, float slope, float* y, int ldy, int64_t M, int Nout, cp_stream_t s);
+
+/* ---- K2: EdgeConv -----------------------------------------------------------------------------
+ * Aggregation half:  y[b,i,c] = lrelu(max_k z[b, idx[g(b), i, k], c] + z[b, i, Co + c]),  z (B,N,2Co).
+ * idx (G, N, K) int32; graph_sel (B) int32 selects the per-RoI graph (pipeline_lm.py:55-57), NULL =>
+ * shared graph 0 (pipeline.py:55).  dtype applies to z and y. */
+int cp_edge_aggregate(const void* z, int dtype, const int32_t* idx, const int32_t* graph_sel, float slope,
+                      void* y, int B, int N, int K, int Co, cp_stream_t s);
+
+/* Fused tcgen05 chain (bf16 operands, fp32 accumulation in TMEM).  One launch does, per tile of 128
+ * nodes:  PROLOGUE -> A tile in shared memory -> up to 3 chained GEMM(+bias+LeakyReLU) layers whose
+ * weights are streamed with bulk-async copies -> OUTPUT.
+ *   prologue CP_PRO_LOAD : A = src[b, n, :C]                                   (bf16 node-major)
+ *            CP_PRO_AGG  : A = lrelu(max_k z[b, idx[n,k], :Co] + z[b, n, Co:])  (EdgeConv aggregation)
+ *            CP_PRO_TAPS : A = [4-tap gather of patches * roi mask | graph_feat] (Index2Feat + concat,
+ *                          pipeline.py:147-164, 278-283)
+ *   output   CP_OUT_BF16 : out (B*N, ld_out) bf16, all Nout columns (EdgeConv [P|Q] table)
+ *            CP_OUT_F32  : out (B*N, ld_out) f32, first n_valid columns (logits)
+ * See DESIGN.md for the tile/pipeline description. */
+enum { CP_PRO_LOAD = 0, CP_PRO_AGG = 1, CP_PRO_TAPS = 2 };
+enum { CP_OUT_BF16 = 0, CP_OUT_F32 = 1 };
+
+typedef struct {
+  const void* w_packed; /* cp_pack_weight image of the (nout, kin) weight */
+  const float* bias;    /* (nout) or NULL */
+  int kin;              /* multiple of 64, <= 512 for layer 0 of TAPS, else <= 256 */
+  int nout;             /* <= 512 for the last layer with CP_OUT_BF16, else <= 256 */
+  int act;              /* 0 none, 1 LeakyReLU */
+  float slope;
+} cp_chain_layer;
+
+typedef struct {
+  int prologue;
+  int B, N;
+  /* LOAD */
+  const void* src; int ld_src; int C;
+  /* AGG */
+  const void* z; int ld_z; int Co; const int32_t* idx; const int32_t* graph_sel; int K; float agg_slope;
+  /* TAPS: patches (B, Hp, Wp, E) bf16 NHWC, ids (B,N) int64, mask (B,N) f32 {0,1}, graph_feat (B,N,Cg) bf16 */
+  const void* patches; int Hp, Wp, E, tap_step; const int64_t* x_id; const int64_t* y_id; const float* mask;
+  const void* graph_feat; int ld_gf; int Cg;
+  /* optional copy of the prologue's A tile (first C / Co channels) to global, bf16 (B*N, ld_a_out) */
+  void* a_out; int ld_a_out;
+  int num_layers;
+  cp_chain_layer layers[3];
+  int out_mode; void* out; int ld_out; int n_valid;
+} cp_chain_params;
+
+int cp_chain_fwd(const cp_chain_params* p, cp_stream_t s);
+
+/* ---- K3: Index2Feat 4-tap integer gather (pipeline.py:156-163) + roi-mask multiply (:280) ------
+ * patches (B, Hp, Wp, E) NHWC in `dtype`; taps (2y,2x),(2y+k,2x),(2y,2x+k),(2y+k,2x+k), channel order
+ * [tap1 | tap2 | tap3 | tap4]; out (B, N, 4E) node-major in `dtype`; mask (B,N) f32 or NULL. */
+int cp_sample_taps(const void* patches, int dtype, int Hp, int Wp, int E, int tap_step, const int64_t* x_id,
+                   const int64_t* y_id, const float* mask, void* out, int B, int N, cp_stream_t s);
+
+/* ---- K4: sign-bit decode ------------------------------------------------------------------------
+ * Init stage (pipeline.py:363-369): logits (B*N, ld) f32 rows = [roi, x_0..x_{L-1}, y_0..y_{L-1}].
+ * Writes roi_bit (B,1,N), planes 0..L-1 of x_bits / y_bits (B, Ltot, N), roi_mask (B,N) f32 {0,1} and
+ * ids (B,N) int64 = sum_i bit_i 2^(L-1-i).  bit = logit > 0  (== sigmoid > 0.5 up to |logit| < 2e-7). */
+int cp_decode_init(const float* logits, int ld, int L, int Ltot, float* roi_bit, float* x_bits, float* y_bits,
+                   float* roi_mask, int64_t* x_id, int64_t* y_id, int B, int N, cp_stream_t s);
+/* Refine stage (pipeline.py:375-381): logits (B*N, ld) rows = [x_new, y_new]; writes plane `plane` of
+ * x_bits / y_bits and updates id = 2*id + bit in place. */
+int cp_decode_refine(const float* logits, int ld, int plane, int Ltot, float* x_bits, float* y_bits,
+                     int64_t* x_id, int64_t* y_id, int B, int N, cp_stream_t s);
+/* Correspondence records, first half of from_id_to_pose (test_network_with_test_data.py:50-66) for the
+ * three calls of test.py:335-368, with roi_xy_ori of bop_dataset_pytorch.py:223-235,266-269:
+ *   u = bbox.x + x_id * bbox.w / S,  v = bbox.y + y_id * bbox.h / S
+ *   flags bit0 = roi logit > 0; bit1 = bit0 & seg[1 (full)][y,x] > 0; bit2 = bit0 & seg[0 (visib)][y,x] > 0
+ * roi_bit (B,1,N) f32 logits, seg (B,2,S,S) f32 logits NCHW, bbox (B,4) f32 [x,y,w,h]. */
+typedef struct { float u, v; uint32_t flags; } cp_corr_record;
+int cp_correspondences(const float* roi_bit, const float* seg, const float* bbox, const int64_t* x_id,
+                       const int64_t* y_id, cp_corr_record* out, int B, int N, int S, cp_stream_t s);
+
+/* Elementwise helpers behind common_ops.py:5-27 and pipeline.py:84-127.
+ * out = sigmoid(x) > thr ? 1 : 0 as f32 (out_dtype 0) or int64 (out_dtype 1). */
+int cp_threshold(const float* x, float thr, int apply_sigmoid, void* out, int out_dtype, int64_t count, cp_stream_t s);
+/* MSB-first code -> id (pipeline.py:72-82; class_id_encoder_decoder.py:17-63).
+ * in element (o, l, i) at in[o*stride_o + l*stride_l + i*stride_i] (f32); digit = binarize ? (in > thr) : in;
+ * out[o*inner + i] = sum_l digit * base^(L-1-l), written as int64 (out_dtype 1) or f32 (out_dtype 0). */
+int cp_bits_to_id(const float* in, int64_t outer, int L, int64_t inner, int64_t stride_o, int64_t stride_l,
+                  int64_t stride_i, int binarize, float thr, int base, void* out, int out_dtype, cp_stream_t s);
+
+/* Inverse of cp_bits_to_id for power-of-two bases (class_id_encoder_decoder.py:65-101):
+ * out[e*L + l] = (ids[e] >> (log2(base)*(L-1-l))) - ((ids[e] >> (log2(base)*(L-l))) << log2(base)), as f32. */
+int cp_id_to_bits(const int64_t* ids, int64_t count, int L, int base, float* out, cp_stream_t s);
+/* CE branch of from_output_to_class_binary_code (common_ops.py:29-38): x viewed as (G, D, inner) f32,
+ * out[g*inner + i] = argmax_d x[g, d, i] (first maximum wins, like numpy.argmax) as int64. */
+int cp_group_argmax(const float* x, int64_t G, int D, int64_t inner, int64_t* out, cp_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHECKERPOSE_B200_H_ */

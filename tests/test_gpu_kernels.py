@@ -1,0 +1,331 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against golden vectors produced by
+the unmodified reference modules and against the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import knn_sets_equal, knn_tie_rows, rel_err, syn
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(scope="module")
+def cp():
+    import checkerpose_b200
+    from checkerpose_b200 import common_ops, head, ops
+    from checkerpose_b200.binary_code_helper import class_id_encoder_decoder as codec
+    from checkerpose_b200.model import pipeline, pipeline_lm
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.ops, ns.head, ns.pipeline, ns.pipeline_lm, ns.common_ops, ns.codec = ops, head, pipeline, pipeline_lm, common_ops, codec
+    ns.pkg = checkerpose_b200
+    assert ops.lib.cp_device_arch() >= 100, "these kernels are built for sm_100a"
+    return ns
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode():
+    from checkerpose_b200 import head
+    head.set_compute_dtype(torch.float32)
+    yield
+    head.set_compute_dtype(torch.float32)
+
+
+def cuda(a, dtype=None):
+    t = torch.as_tensor(np.asarray(a)) if not isinstance(a, torch.Tensor) else a
+    t = t.cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def test_knn_all_fixtures(cp, golden):
+    g = golden("knn")
+    n = 0
+    for key, ref in g.items():
+        if key.startswith("rand"):
+            continue
+        ds, oid, ns, ks = key.split("_")
+        N, K = int(ns[1:]), int(ks[1:])
+        p = syn.p3d_normed_tensor(syn.load_fps_xyz(ds, int(oid), N))
+        idx = cp.pipeline.knn(p.cuda(), K)
+        assert idx.dtype == torch.int64 and idx.shape == (1, N, K)
+        idx = idx[0].cpu().numpy()
+        bad = knn_sets_equal(idx, ref, tie_rows=knn_tie_rows(p, K, 1e-6))
+        assert len(bad) == 0, f"{key}: {len(bad)} rows differ outside 1e-6 ties"
+        assert (idx[:, 0] == np.arange(N)).all()
+        n += 1
+    assert n == 57
+
+
+def test_knn_generic_channels_and_order(cp, golden):
+    g = golden("knn")
+    x = torch.from_numpy(g["rand_c16_n200_k12_x"])
+    idx = cp.pipeline.knn(x.cuda(), 12).cpu().numpy()
+    ref = g["rand_c16_n200_k12"].astype(np.int64)
+    assert np.array_equal(np.sort(idx, -1), np.sort(ref, -1))
+    assert (idx == ref).mean() > 0.999  # nearest-first order, up to fp32 near-ties
+
+
+def test_knn_edge_cases(cp):
+    x = torch.randn(2, 3, 70, generator=torch.Generator().manual_seed(3))
+    for k in (1, 33, 64, 70):
+        if k > 64:
+            with pytest.raises(RuntimeError):
+                cp.pipeline.knn(x.cuda(), k)
+            continue
+        idx = cp.pipeline.knn(x.cuda(), k).cpu()
+        d = ((x[:, :, :, None] - x[:, :, None, :]) ** 2).sum(1)
+        ref = d.topk(k, dim=-1, largest=False)[1]
+        assert torch.equal(torch.sort(idx, -1)[0], torch.sort(ref, -1)[0])
+    with pytest.raises(RuntimeError):
+        cp.pipeline.knn(x, 4)  # CPU tensor: no fallback
+
+
+# ------------------------------------------------------------------------------------------------ K2
+def _sg_module(cp, g, tag, lm):
+    t = lambda k: torch.from_numpy(g[f"sg_{tag}_{k}"])
+    Co, C2 = t("conv.0.weight").shape[:2]
+    idx = t("lm_idx" if lm else "idx").long().cuda()
+    cls = cp.pipeline_lm.StaticGraph_module if lm else cp.pipeline.StaticGraph_module
+    m = cls(C2 // 2, Co, idx, leaky_slope=0.2)
+    m.load_state_dict({k[len(f"sg_{tag}_"):]: torch.from_numpy(v) for k, v in g.items()
+                       if k.startswith(f"sg_{tag}_conv")}, strict=True)
+    return m.cuda().eval(), t
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_static_graph_module_fp32(cp, golden, tag):
+    g = golden("modules")
+    m, t = _sg_module(cp, g, tag, lm=False)
+    y = m(t("x").cuda(), None)
+    assert y.shape == t("y").shape and y.dtype == torch.float32
+    assert rel_err(y.cpu(), t("y")) < 1e-3
+    assert torch.allclose(y.cpu(), t("y"), rtol=1e-4, atol=1e-4)
+    # node-major (permuted view) input takes the zero-copy path and must agree
+    xv = t("x").cuda().permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    assert torch.equal(m(xv, None), y)
+    mlm, _ = _sg_module(cp, g, tag, lm=True)
+    y = mlm(t("x").cuda(), None, t("lm_obj").cuda())
+    assert torch.allclose(y.cpu(), t("lm_y"), rtol=1e-4, atol=1e-4)
+
+
+def test_static_graph_requires_eval_and_cuda(cp, golden):
+    g = golden("modules")
+    m, t = _sg_module(cp, g, "a", lm=False)
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(t("x").cuda(), None)
+    m.eval()
+    with pytest.raises(RuntimeError):
+        m(t("x"), None)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_static_graph_module_bf16(cp, golden, tag):
+    """tcgen05 GEMM + bf16 aggregation vs the reference module: 1e-2 relative (north_star bf16 bar)."""
+    g = golden("modules")
+    m, t = _sg_module(cp, g, tag, lm=False)
+    cp.head.set_compute_dtype(torch.bfloat16)
+    y = m(t("x").cuda(), None)
+    assert y.dtype == torch.float32
+    ref = t("y")
+    scale = ref.abs().max()
+    assert (y.cpu() - ref).abs().max() < 2e-2 * scale, float((y.cpu() - ref).abs().max() / scale)
+    mlm, _ = _sg_module(cp, g, tag, lm=True)
+    y = mlm(t("x").cuda(), None, t("lm_obj").cuda())
+    assert (y.cpu() - t("lm_y")).abs().max() < 2e-2 * scale
+
+
+def test_get_graph_feature(cp, golden):
+    g = golden("modules")
+    y = cp.pipeline.get_graph_feature(cuda(g["ggf_x"]), cuda(g["ggf_idx"]).long(), None)
+    assert np.array_equal(y.cpu().numpy(), g["ggf_y"])
+
+
+# ------------------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("tag,k,fd,ed", [("a", 2, 32, 16), ("b", 2, 256, 64), ("c", 4, 32, 8)])
+def test_index2feat(cp, golden, tag, k, fd, ed):
+    g = golden("modules")
+    t = lambda n: torch.from_numpy(g[f"i2f_{tag}_{n}"])
+    m = cp.pipeline.Index2Feat_module(feat_dim=fd, embed_dim=ed, kernel_size=k)
+    m.load_state_dict({"patch_generator.weight": t("patch_generator.weight"), "patch_generator.bias": t("patch_generator.bias")})
+    m = m.cuda().eval()
+    y = m(t("feat").cuda(), None, t("xid").cuda(), t("yid").cuda())
+    assert y.shape == t("y").shape
+    # the gather itself is an exact copy; the conv before it is cuDNN fp32 (not bit-identical to the CPU conv)
+    assert torch.allclose(y.cpu(), t("y"), rtol=1e-4, atol=1e-5)
+    patches = cp.head.patches_nhwc(m.patch_generator, t("feat").cuda(), torch.float32)
+    taps = cp.ops.sample_taps(patches, t("xid").cuda(), t("yid").cuda(), None, k)
+    B, N = t("xid").shape
+    bi = torch.arange(B).view(B, 1).expand(-1, N)
+    pc = patches.cpu()
+    want = torch.cat([pc[bi, 2 * t("yid") + dy, 2 * t("xid") + dx] for dx, dy in ((0, 0), (0, k), (k, 0), (k, k))], dim=2)
+    assert torch.equal(taps.cpu(), want), "4-tap gather must be bit-exact"
+
+
+def test_mlp_query(cp, golden):
+    g = golden("modules")
+    m = cp.pipeline.MLP_QueryNet(feat_dims=(256, 256, 64), pt_dim=3, out_dim=2, leaky_slope=0.01)
+    m.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("mq_mlps")})
+    y = m.cuda().eval()(cuda(g["mq_x"]), None)
+    assert torch.allclose(y.cpu(), torch.from_numpy(g["mq_y"]), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ K4
+def test_decode_functions(cp, golden):
+    g = golden("decode")
+    cpb = torch.from_numpy(g["code_prob"])
+    safe = (cpb.abs() > 1e-4)            # north_star: exact except logits within 1e-4 of the threshold
+    P = cp.pipeline
+    x = cpb.cuda()
+    m = P.from_mask_prob_to_mask(x).cpu()
+    assert m.dtype == torch.float32 and torch.equal(m[safe], torch.from_numpy(g["mask"])[safe])
+    safe_kp = safe.all(dim=1)
+    ids = P.from_code_prob_to_id(x).cpu()
+    assert ids.dtype == torch.int64 and torch.equal(ids[safe_kp], torch.from_numpy(g["code_prob_id"])[safe_kp])
+    b = P.from_bit_prob_to_id(x[:, 0:1]).cpu()
+    assert torch.equal(b[safe[:, 0]], torch.from_numpy(g["bit_prob_id"])[safe[:, 0]])
+    assert np.array_equal(P.from_gt_code_to_id(torch.sigmoid(cpb).cuda()).cpu().numpy()[safe_kp], g["gt_code_id"][safe_kp])
+    assert np.array_equal(P.from_gt_bit_to_id(torch.sigmoid(cpb[:, 0:1]).cuda()).cpu().numpy()[safe[:, 0]], g["gt_bit_id"][safe[:, 0]])
+    assert np.array_equal(P.from_code_to_id(cuda(g["code"])).cpu().numpy(), g["code_id"])
+
+
+def test_common_ops(cp, golden):
+    g = golden("decode")
+    x = cuda(g["code_prob"])
+    co = cp.common_ops
+    for thr in (0.5, 0.3, 0.9):
+        logit_thr = float(np.log(thr / (1 - thr)))
+        safe = np.abs(g["code_prob"] - logit_thr) > 1e-4
+        a = co.from_output_to_class_mask(x, thershold=thr)
+        assert isinstance(a, np.ndarray) and a.dtype == np.float64
+        assert np.array_equal(a[safe], g[f"co_mask_{thr}"][safe])
+        b = co.from_output_to_class_mask_torch(x, thershold=thr)
+        assert b.is_cuda and np.array_equal(b.cpu().numpy()[safe], g[f"co_mask_torch_{thr}"][safe])
+        c = co.from_output_to_class_binary_code(x, "BCE", thershold=thr)
+        assert np.array_equal(c[safe], g[f"co_code_bce_{thr}"][safe])
+    ce = co.from_output_to_class_binary_code(cuda(g["co_ce_in"]), "CE", divided_num_each_interation=2, binary_code_length=16)
+    assert ce.shape == g["co_code_ce"].shape and np.array_equal(ce, g["co_code_ce"])
+    assert tuple(co.get_batch_size(0.75, 32)) == tuple(g["co_batch_size"])
+    assert co.from_dim_str_to_tuple("256_256_64") == tuple(g["co_dim_tuple"]) and co.from_dim_str_to_tuple(None) is None
+
+
+def test_codec(cp, golden):
+    g = golden("decode")
+    c = cp.codec
+    a = c.class_code_vecs_to_class_id_vec(g["cc_vecs"])
+    assert a.dtype == np.float64 and np.array_equal(a, g["cc_vecs_id"])
+    assert np.array_equal(c.class_code_images_to_class_id_image(g["cc_hwc"]), g["cc_hwc_id"])
+    t = c.class_code_images_to_class_id_image_torch(cuda(g["cc_chw"]))
+    assert t.dtype == torch.float32 and np.array_equal(t.cpu().numpy(), g["cc_chw_id"])
+    t = c.class_code_images_to_class_id_image_torch_batch(cuda(g["cc_bchw"]))
+    assert t.dtype == torch.int64 and np.array_equal(t.cpu().numpy(), g["cc_bchw_id"])
+    assert np.array_equal(c.class_id_vec_to_class_code_vecs(g["cc_ids"], class_base=2, iteration=6), g["cc_ids_code"])
+    assert np.array_equal(c.class_id_image_to_class_code_images(g["cc_idimg"], 2, 8, 256), g["cc_idimg_code"])
+    assert c.code_to_id([1, 0, 1, 1, 0]) == int(g["cc_code_to_id"]) and c.str_code_to_id("10110") == int(g["cc_str_code_to_id"])
+    with pytest.raises(ValueError):
+        c.class_id_image_to_class_code_images(g["cc_idimg"], 2, 7, 256)
+
+
+def test_correspondences(cp, golden):
+    g = golden("correspondences")
+    xyz = syn.load_fps_xyz("lmo", 1, 300)
+    B, N, S = 3, 300, 64
+    roi = torch.stack([torch.from_numpy(g[f"c{c}_roi_logit"]) for c in range(B)]).float().view(B, 1, N)
+    seg = torch.stack([torch.from_numpy(g[f"c{c}_seg_logit"]) for c in range(B)]).float()
+    bbox = torch.stack([torch.from_numpy(g[f"c{c}_bbox"]) for c in range(B)]).float()
+    xid = torch.stack([torch.from_numpy(g[f"c{c}_xid"]) for c in range(B)]).long()
+    yid = torch.stack([torch.from_numpy(g[f"c{c}_yid"]) for c in range(B)]).long()
+    rec = cp.ops.correspondences(roi.cuda(), seg.cuda(), bbox.cuda(), xid.cuda(), yid.cuda())
+    uv, flags = cp.ops.split_correspondences(rec)
+    uv, flags = uv.cpu().numpy(), flags.cpu().numpy()
+    for c in range(B):
+        for bit, tag in ((1, "all"), (2, "full"), (4, "visib")):
+            m = (flags[c] & bit) != 0
+            assert np.array_equal(xyz[m], g[f"c{c}_{tag}_p3d"]), "valid set must match the reference exactly"
+            assert np.allclose(uv[c][m], g[f"c{c}_{tag}_p2d"], rtol=1e-6, atol=0)  # f32 record vs f64 grid
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 chain
+def _bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("C,Nout,N,B", [(64, 128, 300, 2), (256, 512, 128, 3), (128, 64, 257, 1), (256, 16, 512, 2)])
+def test_chain_gemm_exact(cp, C, Nout, N, B):
+    """LOAD -> one GEMM: with bf16-representable operands the fp32-accumulated tcgen05 result must equal
+    a float64 matmul to fp32 rounding -- any descriptor / swizzle / TMEM-lane mistake shows up here."""
+    ops = cp.ops
+    g = torch.Generator().manual_seed(C + Nout)
+    x = _bf16_round(torch.randn(B, N, C, generator=g))
+    w = _bf16_round(torch.randn(Nout, C, generator=g) / C ** 0.5)
+    bias = torch.randn(Nout, generator=g)
+    ref = (x.double() @ w.double().t() + bias.double())
+    wp = ops.pack_weight(w.cuda())
+    # fp32 output (first n_valid columns)
+    nv = min(Nout, 256)
+    if Nout <= 256:
+        out = torch.full((B, N, Nout), float("nan"), device="cuda")
+        ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x.cuda().to(torch.bfloat16),
+                      layers=[ops.chain_layer(wp, bias.cuda(), C, Nout, False, 0.0)], out=out, out_mode=ops.OUT_F32, n_valid=nv)
+        torch.cuda.synchronize()
+        assert torch.allclose(out.cpu().double(), ref, rtol=1e-5, atol=1e-5), float((out.cpu().double() - ref).abs().max())
+    # bf16 output with LeakyReLU
+    out = torch.empty((B, N, Nout), dtype=torch.bfloat16, device="cuda")
+    ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x.cuda().to(torch.bfloat16),
+                  layers=[ops.chain_layer(wp, bias.cuda(), C, Nout, True, 0.2)], out=out, out_mode=ops.OUT_BF16)
+    want = torch.nn.functional.leaky_relu(ref, 0.2)
+    assert torch.allclose(out.cpu().double(), want, rtol=1e-2, atol=1e-2)
+
+
+def test_chain_three_layers(cp):
+    """LOAD -> 256->256 (LReLU) -> 256->64 (LReLU) -> 64->2: the MLP_QueryNet chain; activations are
+    re-quantised to bf16 between layers exactly as the kernel does."""
+    ops = cp.ops
+    g = torch.Generator().manual_seed(5)
+    B, N = 2, 384
+    x = _bf16_round(torch.randn(B, N, 256, generator=g))
+    ws = [_bf16_round(torch.randn(o, i, generator=g) * (2.0 / i) ** 0.5) for o, i in ((256, 256), (64, 256), (2, 64))]
+    bs = [torch.randn(o, generator=g) * 0.1 for o in (256, 64, 2)]
+    h = x.double()
+    for li, (w, b) in enumerate(zip(ws, bs)):
+        h = h @ w.double().t() + b.double()
+        if li < 2:
+            h = _bf16_round(torch.nn.functional.leaky_relu(h, 0.01).float()).double()
+    layers = [ops.chain_layer(ops.pack_weight(w.cuda()), b.cuda(), w.shape[1], w.shape[0], li < 2, 0.01)
+              for li, (w, b) in enumerate(zip(ws, bs))]
+    out = torch.zeros((B, N, 16), device="cuda")
+    ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x.cuda().to(torch.bfloat16), layers=layers, out=out,
+                  out_mode=ops.OUT_F32, n_valid=2)
+    got = out[:, :, :2].cpu().double()
+    # bf16 re-quantisation of intermediates can differ by one ulp where fp32 sums differ in the last bit
+    assert (got - h).abs().max() < 2e-2 * h.abs().max(), float((got - h).abs().max())
+
+
+def test_chain_agg_prologue(cp):
+    """AGG prologue (EdgeConv aggregation in registers) + GEMM vs the same maths in float64."""
+    ops = cp.ops
+    g = torch.Generator().manual_seed(6)
+    B, N, Co, K = 3, 200, 256, 20
+    z = _bf16_round(torch.randn(B, N, 2 * Co, generator=g))
+    idx = torch.randint(0, N, (2, N, K), generator=g).int()
+    sel = torch.tensor([1, 0, 1]).int()
+    w = _bf16_round(torch.randn(512, Co, generator=g) / 16)
+    gat = z[:, :, :Co][torch.arange(B)[:, None, None], idx[sel.long()].long()]      # (B,N,K,Co)
+    a = torch.nn.functional.leaky_relu(gat.max(dim=2)[0] + z[:, :, Co:], 0.2)
+    a_bf = _bf16_round(a)
+    ref = a_bf.double() @ w.double().t()
+    out = torch.empty((B, N, 512), dtype=torch.bfloat16, device="cuda")
+    a_out = torch.empty((B, N, Co), dtype=torch.bfloat16, device="cuda")
+    ops.chain_fwd(prologue=ops.PRO_AGG, B=B, N=N, z=z.cuda().to(torch.bfloat16), idx32=idx.cuda(), graph_sel=sel.cuda(),
+                  agg_slope=0.2, a_out=a_out, layers=[ops.chain_layer(ops.pack_weight(w.cuda()), None, Co, 512, False, 0.0)],
+                  out=out, out_mode=ops.OUT_BF16)
+    assert torch.equal(a_out.cpu().float(), a_bf), "aggregated tile must be bit-exact in bf16"
+    assert torch.allclose(out.cpu().double(), ref, rtol=1e-2, atol=1e-2)
+    # the SIMT aggregation kernel computes the same thing
+    y = ops.edge_aggregate(z.cuda().to(torch.bfloat16), idx.cuda(), sel.cuda(), 0.2)
+    assert torch.equal(y.cpu().float(), a_bf)

@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the GNN keypoint head (BASELINE.json metric: RoIs/sec, 4096-keypoint head).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the whole post-backbone head (init net, 3 refine stages incl. the cuDNN image
+branch, decode, correspondence records) over a batch of synthetic RoIs.  Workload at every N:
+BASELINE.json configs[2], "full progressive 512->4096 keypoint GNN head, batch 256 RoIs, bf16" -- 256
+RoIs PER GPU (weak scaling: the RoI batch is sharded, weights and graph replicated), and with N > 1 one
+NCCL all-gather of the decoded correspondence records per step inside the timed region.
+
+Prints ONE JSON line (rank 0).  ``value`` = RoIs/s with inputs resident in HBM; ``e2e`` = the same through
+the public module API from pinned host buffers (H2D of the feature maps + D2H of the records every step);
+``roofline`` = the dominant kernel (fused EdgeConv aggregation + [P|Q] GEMM, chain_kernel<AGG>) timed live
+with CUDA events on its launching stream; ``cpu_baseline`` = the CPU oracle port of the reference head on
+this box's host cores over a bounded sample.  ``--impl reference`` times only that CPU port.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+METRIC = "RoIs/sec (4096-kpt GNN head)"
+UNIT = "RoIs/s"
+NPOINT, GRAPH_K = 4096, 20
+DATASET, OBJ_ID = "lmo", 1
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU port of the reference head (oracle/) -- the baseline, timed on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_rois_per_s(steps, warmup, rois_per_step=1, budget_s=None):
+    from checkerpose_b200 import synthetic as syn
+    from oracle import checkerpose_oracle as orc
+    torch.set_grad_enabled(False)
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1234 + 2)
+    p3d = syn.p3d_normed_tensor(syn.load_fps_xyz(DATASET, OBJ_ID, NPOINT))
+    sd = syn.synthetic_state_dict(syn.head_param_spec(NPOINT), g)
+    feats = syn.synthetic_features(rois_per_step, g)
+    idx = orc.knn(p3d, GRAPH_K)
+    times = []
+    t_start = time.perf_counter()
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.pose_head(feats, sd, idx, [idx] * 3, NPOINT)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        if budget_s is not None and times and time.perf_counter() - t_start > budget_s:
+            break
+    total = sum(times)
+    return rois_per_step * len(times) / total, len(times), total / len(times) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    v, n, ms = cpu_reference_rois_per_s(args.steps, args.warmup, rois_per_step=1)
+    sample = f"{n} timed steps x 1 RoI (N={NPOINT}, K={GRAPH_K}) of the same workload, fp32, torch CPU ops, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full progressive head, N=4096 keypoints, K=20, 3 refine stages (BASELINE.json configs[2]); CPU port of the reference (oracle/), 1 RoI per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from checkerpose_b200 import dist as cpdist, head, ops, synthetic as syn
+    from checkerpose_b200.model import init, pipeline
+    from checkerpose_b200.model.backbone import FeatureListBackbone
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU port"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    head.set_compute_dtype(dtype)
+    B, N = args.batch, NPOINT
+
+    g = torch.Generator().manual_seed(1234 + 2)
+    p3d = syn.p3d_normed_tensor(syn.load_fps_xyz(DATASET, OBJ_ID, N)).to(dev)
+    sd = syn.synthetic_state_dict(syn.head_param_spec(N), g)
+    inet = init.InitNet_GNN(npoint=N, p3d_normed=p3d, res_log2=3, backbone_name="hrnet_w18", pretrain_backbone=False,
+                            max_batch_size=B, num_graph_module=2, graph_k=GRAPH_K, img_backbone=FeatureListBackbone())
+    net = pipeline.PoseNet_GNNskip(inet, npoint=N, p3d_normed=p3d, res_log2=6, num_filters=256, max_batch_size=B,
+                                   local_k=2, leaky_slope=0.01, num_graph_module=3, graph_k=GRAPH_K)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+
+    # synthetic RoI batch, distinct per rank and per RoI (0.5 GB in bf16: larger than the 126 MB L2)
+    gg = torch.Generator(device=dev).manual_seed(4321 + rank)
+    feats = [torch.relu(torch.randn(B, c, s, s, generator=gg, device=dev)).to(dtype)
+             for c, s in zip(syn.HRNET_W18_DIMS, syn.HRNET_W18_SIZES)]
+    bbox = syn.synthetic_bboxes(B, torch.Generator().manual_seed(99 + rank)).to(dev)
+    pexp = p3d.expand(B, -1, -1)
+
+    def step(f):
+        out, corr = net.forward_with_correspondences(f, pexp, bbox)
+        if world > 1:
+            corr = cpdist.gather_correspondences(corr)
+        return out, corr
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nwarm = args.warmup if args.profile else max(args.warmup, 3)
+    for _ in range(nwarm):
+        step(feats)
+    barrier()
+
+    # ---------------- timed region: inputs resident in HBM ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.chain_event_log = []
+    n0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(feats)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ops.launch_count - n0
+    log, ops.chain_event_log = ops.chain_event_log, None
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # dominant kernel: chain_kernel<AGG> 256 -> [P|Q] 512 (EdgeConv aggregation fused with the next layer's GEMM)
+    dom = [(a.elapsed_time(b)) for sig, a, b in log if sig[0] == ops.PRO_AGG and sig[2] == (512,) and sig[1] == 256]
+    allchain = sum(a.elapsed_time(b) for _, a, b in log)
+    peak, peak_src = load_peaks()
+    s_el = 2 if dtype == torch.bfloat16 else 4
+    alg_bytes = B * (N * 256 * s_el + N * 256 * s_el)          # N*C*s + N*C'*s per RoI-layer
+    roof = None
+    if dom:
+        avg_ms = sum(dom) / len(dom)
+        ach = alg_bytes / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "chain_kernel<AGG> (EdgeConv max-aggregation + [P|Q] GEMM, C=256)", "achieved": ach,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "avg_launch_ms": avg_ms, "launches_per_step": len(dom) / args.steps, "algorithmic_bytes_per_launch": alg_bytes,
+                "share_of_step": sum(dom) / ms_total if world == 1 else None, "all_chain_kernels_share_of_step": allchain / ms_total if world == 1 else None}
+
+    if args.profile:   # under ncu: no e2e / CPU legs, numbers printed here are NOT bench values
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": launches, "roofline": roof}))
+        return
+
+    # ---------------- e2e: pinned host buffers -> public API -> host, every step ----------------
+    host_feats = [f.cpu().pin_memory() for f in feats]
+    dbuf = [[torch.empty_like(f) for f in feats] for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    h2d_bytes = sum(f.numel() * f.element_size() for f in feats)
+    host_corr = torch.empty((B * world if world > 1 else B, N, 3), dtype=torch.int32).pin_memory()
+    d2h_bytes = host_corr.numel() * 4
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for d, h in zip(dbuf[s], host_feats):
+                d.copy_(h, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_run(nsteps):
+        main = torch.cuda.current_stream()
+        for s in range(2):
+            consumed[s].record(main)
+        upload(0)
+        for i in range(nsteps):
+            if i + 1 < nsteps:
+                upload(i + 1)                       # overlap the next step's H2D with this step's compute
+            main.wait_event(ready[i % 2])
+            _, corr = step(dbuf[i % 2])
+            consumed[i % 2].record(main)
+            host_corr.copy_(corr, non_blocking=True)
+        main.synchronize()
+
+    e2e_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    e2e_run(args.steps)
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
+
+    # ---------------- GNN-only (no cuDNN image branch): reuse cached image features ----------------
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, n, ms = cpu_reference_rois_per_s(steps=8, warmup=1, rois_per_step=1, budget_s=20.0)
+        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{n} x 1 RoI of the same workload (N={N}) through oracle/ on torch CPU fp32, {ms:.0f} ms each"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": nwarm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "full progressive head (init net + 3 refine stages + decode + correspondences), N=4096 keypoints, "
+                                   "K=20, 256 RoIs per GPU (BASELINE.json configs[2])",
+                       "rois_per_gpu": B, "npoint": N, "graph_k": GRAPH_K, "object": f"{DATASET}/{OBJ_ID}",
+                       "image_branch": "included (cuDNN, library part of the path)",
+                       "l2": "inputs (0.5 GB/step) and intermediates (>1 GB) exceed the 126 MB L2; no explicit flush",
+                       "collective": "all_gather_into_tensor of correspondence records per step" if world > 1 else "none (1 GPU)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "note": "pinned host feature maps -> PoseNet_GNNskip.forward_with_correspondences -> pinned host records; "
+                            "next step's H2D overlaps compute on a copy stream"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="RoIs per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: timed loop only, warm-up exactly --warmup")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

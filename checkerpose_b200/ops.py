@@ -19,6 +19,8 @@ OUT_BF16, OUT_F32 = 0, 1
 
 #: number of kernel launches issued through this module (bench.py reports it as ``gpu_launches``)
 launch_count = 0
+#: when set to a list, chain_fwd appends (signature, start_event, end_event) per launch (bench.py roofline)
+chain_event_log = None
 
 
 def _count(n=1):
@@ -204,8 +206,14 @@ def sample_taps(patches_nhwc, x_id, y_id, mask, tap_step, out=None):
 
 
 # ------------------------------------------------------------------------------- tcgen05 chain
+class _Layer(ChainLayer):
+    """ChainLayer that keeps its tensors alive until the launch has been issued."""
+
+
 def chain_layer(w_packed, bias, kin, nout, act, slope) -> ChainLayer:
-    return ChainLayer(C.c_void_p(w_packed.data_ptr()), _p(bias), int(kin), int(nout), int(bool(act)), float(slope))
+    L = _Layer(C.c_void_p(w_packed.data_ptr()), _p(bias), int(kin), int(nout), int(bool(act)), float(slope))
+    L._keepalive = (w_packed, bias)
+    return L
 
 
 def chain_fwd(*, prologue, B, N, layers, out, out_mode, n_valid=0,
@@ -238,7 +246,16 @@ def chain_fwd(*, prologue, B, N, layers, out, out_mode, n_valid=0,
     for i, L in enumerate(layers):
         p.layers[i] = L
     p.out_mode, p.out, p.ld_out, p.n_valid = out_mode, _p(out), out.shape[-1], int(n_valid)
-    check(lib.cp_chain_fwd(C.byref(p), _stream()), "cp_chain_fwd")
+    if chain_event_log is not None:
+        # bench.py: CUDA events on the launching stream around this one launch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.cp_chain_fwd(C.byref(p), _stream()), "cp_chain_fwd")
+        e1.record()
+        kin0 = layers[0].kin
+        chain_event_log.append(((prologue, kin0, tuple(L.nout for L in layers), out_mode, B, N), e0, e1))
+    else:
+        check(lib.cp_chain_fwd(C.byref(p), _stream()), "cp_chain_fwd")
     _count()
     return out
 

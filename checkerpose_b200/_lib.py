@@ -49,6 +49,8 @@ SIGNATURES = {
     "cp_edge_aggregate": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_f32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cp_chain_fwd": (c_i32, [C.POINTER(ChainParams), c_vp]),
     "cp_sample_taps": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "cp_upsample2x_cat_nhwc": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32,
+                                       c_i32, c_i32, c_vp]),
     "cp_decode_init": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "cp_decode_refine": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "cp_correspondences": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),

@@ -120,9 +120,9 @@ __device__ __forceinline__ void fill_agg(uint8_t* A, const cp_chain_params& p, i
       const int i = n0 + r;
       const int32_t* nb = idx_g + (size_t)i * K;
       const bf16* zc = zb + chunk * 8;
-      // self is always a neighbour, so starting from row i keeps the max exact and avoids -inf seeds
-      uint4 m = ldg_nc_v4(zc + (size_t)i * p.ld_z);
-      int k = 0;
+      // seed with the first neighbour (no -inf constants; correct for graphs without self loops too)
+      uint4 m = ldg_nc_v4(zc + (size_t)__ldg(nb) * p.ld_z);
+      int k = 1;
       for (; k + 4 <= K; k += 4) {
         const int j0 = __ldg(nb + k), j1 = __ldg(nb + k + 1), j2 = __ldg(nb + k + 2), j3 = __ldg(nb + k + 3);
         const uint4 v0 = ldg_nc_v4(zc + (size_t)j0 * p.ld_z);

@@ -1,0 +1,114 @@
+// Byte movers of the image branch that sit between the cuDNN convolutions.
+//
+// cp_upsample2x_cat_nhwc: nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) applied to the
+// channel concatenation torch.cat([img_feat, skip], dim=1) of checkerpose/model/pipeline.py:372-373 and
+// :201, in one pass over NHWC tensors: the (B, C1+C2, H, W) concat is never materialised and the
+// (B, 2H, 2W, C1+C2) result is written once with 128-bit stores.  HBM-bound: bytes = out + in.
+#include "common.cuh"
+
+using bf16 = __nv_bfloat16;
+
+namespace {
+
+struct Src {
+  const void* p;
+  int64_t sb, sh, sw;  // element strides of batch / row / column; channels are contiguous
+  int C;
+};
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  __device__ static void load(const bf16* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static void store(bf16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_cat_nhwc_kernel(Src a, Src b, T* __restrict__ out, int B, int H, int W, float scale_h, float scale_w) {
+  constexpr int V = Vec<T>::N;
+  const int Ct = a.C + b.C;
+  const int cv_per_px = Ct / V;
+  const int OH = 2 * H, OW = 2 * W;
+  const int64_t total = (int64_t)B * OH * OW * cv_per_px;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(e % cv_per_px);
+    int64_t r = e / cv_per_px;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const int bi = (int)(r / OH);
+    // same arithmetic as ATen's upsample_bilinear2d with align_corners=True (accumulation type float)
+    const float hr = scale_h * (float)oy, wr = scale_w * (float)ox;
+    const int h1 = (int)hr, w1 = (int)wr;
+    const int h1p = (h1 < H - 1) ? 1 : 0, w1p = (w1 < W - 1) ? 1 : 0;
+    const float h1l = hr - (float)h1, h0l = 1.f - h1l;
+    const float w1l = wr - (float)w1, w0l = 1.f - w1l;
+    int c = cv * V;
+    const Src& s = (c < a.C) ? a : b;
+    if (c >= a.C) c -= a.C;
+    const T* base = reinterpret_cast<const T*>(s.p) + (int64_t)bi * s.sb + (int64_t)h1 * s.sh + (int64_t)w1 * s.sw + c;
+    float v00[V], v01[V], v10[V], v11[V], o[V];
+    Vec<T>::load(base, v00);
+    Vec<T>::load(base + w1p * s.sw, v01);
+    Vec<T>::load(base + h1p * s.sh, v10);
+    Vec<T>::load(base + h1p * s.sh + w1p * s.sw, v11);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o[i] = h0l * (w0l * v00[i] + w1l * v01[i]) + h1l * (w0l * v10[i] + w1l * v11[i]);
+    Vec<T>::store(out + e * V, o);
+  }
+}
+
+}  // namespace
+
+extern "C" int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_sw, int Ca, const void* b,
+                                      int64_t b_sb, int64_t b_sh, int64_t b_sw, int Cb, int dtype, void* out, int B,
+                                      int H, int W, cp_stream_t s) {
+  CP_REQUIRE(a && out && B > 0 && H > 0 && W > 0 && Ca > 0 && Cb >= 0, CP_E_INVALID, "cp_upsample2x_cat_nhwc: bad arguments");
+  CP_REQUIRE(Cb == 0 || b, CP_E_INVALID, "cp_upsample2x_cat_nhwc: second source is NULL but Cb=%d", Cb);
+  const int V = dtype == CP_F32 ? 4 : 8;
+  CP_REQUIRE(dtype == CP_F32 || dtype == CP_BF16, CP_E_INVALID, "cp_upsample2x_cat_nhwc: bad dtype %d", dtype);
+  CP_REQUIRE(Ca % V == 0 && Cb % V == 0 && a_sb % V == 0 && a_sh % V == 0 && a_sw % V == 0 && b_sb % V == 0 &&
+                 b_sh % V == 0 && b_sw % V == 0,
+             CP_E_UNSUPPORTED, "cp_upsample2x_cat_nhwc: channels and strides must be multiples of %d elements", V);
+  CP_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)out & 15) == 0 && (Cb == 0 || ((uintptr_t)b & 15) == 0), CP_E_INVALID,
+             "cp_upsample2x_cat_nhwc: pointers must be 16-byte aligned");
+  Src sa{a, a_sb, a_sh, a_sw, Ca}, sb{b, b_sb, b_sh, b_sw, Cb};
+  // align_corners=True: scale = (in - 1) / (out - 1)
+  const float sh = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
+  const float sw = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
+  const int64_t total = (int64_t)B * 2 * H * 2 * W * ((Ca + Cb) / V);
+  int64_t g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  if (dtype == CP_F32)
+    upsample2x_cat_nhwc_kernel<float><<<(int)g, 256, 0, (cudaStream_t)s>>>(sa, sb, (float*)out, B, H, W, sh, sw);
+  else
+    upsample2x_cat_nhwc_kernel<bf16><<<(int)g, 256, 0, (cudaStream_t)s>>>(sa, sb, (bf16*)out, B, H, W, sh, sw);
+  CP_CHECK_LAUNCH("cp_upsample2x_cat_nhwc");
+  return CP_OK;
+}

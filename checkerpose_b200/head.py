@@ -82,17 +82,22 @@ def _param_fingerprint(module: nn.Module):
 
 
 class PrepCache:
-    """Lazily (re)built prepared weights, invalidated when parameters change or move."""
+    """Lazily (re)built prepared weights.  The cache lives ON the owning module (so it dies with it -- a
+    global table keyed by ``id()`` / ``data_ptr()`` would hand a new module the stale weights of a freed
+    one whose addresses were recycled) and is invalidated when parameters change version or move."""
 
-    def __init__(self):
-        self._store = {}
+    _ATTR = "_cp_prepared"
 
     def get(self, owner: nn.Module, key, builder):
-        fp = (_param_fingerprint(owner), key)
-        hit = self._store.get(id(owner))
+        store = owner.__dict__.get(self._ATTR)
+        if store is None:
+            store = {}
+            owner.__dict__[self._ATTR] = store
+        fp = _param_fingerprint(owner)
+        hit = store.get(key)
         if hit is None or hit[0] != fp:
             hit = (fp, builder())
-            self._store[id(owner)] = hit
+            store[key] = hit
         return hit[1]
 
 
@@ -110,20 +115,17 @@ def prepared_linear(lin: nn.Module, dtype) -> PreparedLinear:
 
 
 class GraphTable:
-    """int32 copy of a module's kNN index table: (G,N,K); G=1 for the single-object nets."""
-
-    _cache = {}
+    """int32 copy of a module's kNN index table: (G,N,K); G=1 for the single-object nets.  Cached as an
+    attribute of the index tensor itself (never in a table keyed by a recyclable address)."""
 
     @classmethod
     def get(cls, knn_idx: torch.Tensor, device) -> torch.Tensor:
-        key = (knn_idx.data_ptr(), knn_idx._version, tuple(knn_idx.shape), str(device))
-        hit = cls._cache.get(key)
-        if hit is None:
-            hit = knn_idx.to(device=device, dtype=torch.int32).contiguous()
-            if len(cls._cache) > 256:
-                cls._cache.clear()
-            cls._cache[key] = hit
-        return hit
+        device = torch.device(device)
+        hit = getattr(knn_idx, "_cp_idx32", None)
+        if hit is None or hit[0] != knn_idx._version or hit[1].device != device:
+            hit = (knn_idx._version, knn_idx.to(device=device, dtype=torch.int32).contiguous())
+            knn_idx._cp_idx32 = hit
+        return hit[1]
 
 
 def graph_select(knn_idx: torch.Tensor, obj_ids, batch: int, device):
@@ -225,7 +227,11 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
 # image branch helpers (library convolutions)
 # --------------------------------------------------------------------------------------------------
 class _FoldedSeq:
-    """bf16, channels_last, BN-folded functional copy of a conv stack (up_net block / single conv)."""
+    """bf16, channels_last, BN-folded functional copy of a conv stack (up_net block / single conv).
+    Convolutions run on cuDNN (library part of the path); the bilinear x2 upsampling of the concatenated
+    skip connection runs on cp_upsample2x_cat_nhwc (one pass, no materialised concat)."""
+
+    _fused_relu_ok = None   # torch.cudnn_convolution_relu availability, probed on first use
 
     def __init__(self, module):
         mods = list(module) if isinstance(module, nn.Sequential) else [module]
@@ -247,31 +253,60 @@ class _FoldedSeq:
                     b = sh if b is None else b * sc + sh
                     i += 1
                 kind = "convT" if isinstance(m, nn.ConvTranspose2d) else "conv"
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                if relu:
+                    i += 1
                 self.ops.append((kind, w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
-                                 None if b is None else b.to(torch.bfloat16), m))
+                                 None if b is None else b.to(torch.bfloat16), m, relu))
             elif isinstance(m, nn.ReLU):
-                self.ops.append(("relu", None, None, m))
+                self.ops.append(("relu", None, None, m, False))
             elif isinstance(m, nn.LeakyReLU):
-                self.ops.append(("lrelu", None, None, m))
+                self.ops.append(("lrelu", None, None, m, False))
             elif isinstance(m, nn.UpsamplingBilinear2d):
-                self.ops.append(("up", None, None, m))
+                if float(m.scale_factor) != 2.0:
+                    raise RuntimeError("image branch: only UpsamplingBilinear2d(scale_factor=2) is supported")
+                self.ops.append(("up", None, None, m, False))
             else:
                 raise RuntimeError(f"unsupported layer in image branch: {type(m).__name__}")
             i += 1
 
-    def __call__(self, x):
-        x = x.contiguous(memory_format=torch.channels_last)
-        for kind, w, b, m in self.ops:
+    @classmethod
+    def _conv_relu(cls, x, w, b, m):
+        if cls._fused_relu_ok is not False and b is not None and m.groups == 1:
+            try:
+                y = torch.cudnn_convolution_relu(x, w, b, m.stride, m.padding, m.dilation, m.groups)
+                cls._fused_relu_ok = True
+                return y
+            except (RuntimeError, AttributeError):
+                cls._fused_relu_ok = False
+        return torch.relu_(F.conv2d(x, w, b, stride=m.stride, padding=m.padding, dilation=m.dilation, groups=m.groups))
+
+    def __call__(self, x, skip=None):
+        cl = torch.channels_last
+        start = 0
+        if self.ops[0][0] == "up":
+            a = x.contiguous(memory_format=cl)
+            s = None if skip is None else skip.contiguous(memory_format=cl)
+            x = ops.upsample2x_cat(a, s)
+            start = 1
+        else:
+            if skip is not None:
+                x = torch.cat([x, skip], dim=1)
+            x = x.contiguous(memory_format=cl)
+        for kind, w, b, m, relu in self.ops[start:]:
             if kind == "conv":
-                x = F.conv2d(x, w, b, stride=m.stride, padding=m.padding)
+                x = self._conv_relu(x, w, b, m) if relu else F.conv2d(x, w, b, stride=m.stride, padding=m.padding,
+                                                                      dilation=m.dilation, groups=m.groups)
             elif kind == "convT":
                 x = F.conv_transpose2d(x, w, b, stride=m.stride, padding=m.padding, output_padding=m.output_padding)
+                if relu:
+                    x = torch.relu_(x)
             elif kind == "relu":
                 x = torch.relu_(x)
             elif kind == "lrelu":
                 x = F.leaky_relu(x, m.negative_slope)
             else:
-                x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+                x = ops.upsample2x_cat(x.contiguous(memory_format=cl), None)
         return x
 
 
@@ -280,11 +315,14 @@ def _bf16_module(module):
     return _PREP.get(module, ("bf16seq",), lambda: _FoldedSeq(module))
 
 
-def image_block(module, x, dtype):
-    """Run an image-branch block (up_net[i], patch_generator, seg_block) in ``dtype`` on cuDNN."""
+def image_block(module, x, dtype, skip=None):
+    """Run an image-branch block (up_net[i], patch_generator, seg_block) in ``dtype``; ``skip`` is concatenated
+    to ``x`` along the channels first (pipeline.py:372)."""
     with _exact_fp32_convs(dtype == torch.float32):
         if dtype == torch.bfloat16:
-            return _bf16_module(module)(x.to(torch.bfloat16))
+            return _bf16_module(module)(x.to(torch.bfloat16), None if skip is None else skip.to(torch.bfloat16))
+        if skip is not None:
+            x = torch.cat([x.float(), skip.float()], dim=1)
         return module(x.float())
 
 
@@ -387,10 +425,7 @@ def pose_head_forward(net, img_feats, obj_ids=None, stage=None, dtype=None, bbox
     ops.decode_init(logits0, L0, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id)
     img_feat = feat_last
     for i in range(nact):
-        if i > 0:
-            skip = img_feats[-i - 1]
-            img_feat = torch.cat([img_feat, skip.to(img_feat.dtype)], dim=1)
-        img_feat = image_block(net.up_net[i], img_feat, dtype)
+        img_feat = image_block(net.up_net[i], img_feat, dtype, skip=img_feats[-i - 1] if i > 0 else None)
         logits, gfeat = refine_node_major(net.refine_net[i], img_feat, gfeat, roi_mask, x_id, y_id, obj_ids, dtype)
         ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id)
     seg = image_block(net.seg_block, img_feat, dtype).float().contiguous()

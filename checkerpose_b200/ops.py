@@ -205,6 +205,30 @@ def sample_taps(patches_nhwc, x_id, y_id, mask, tap_step, out=None):
     return out
 
 
+def _nhwc_strides(t):
+    """(B,C,H,W) tensor whose channel stride is 1 -> element strides (sb, sh, sw)."""
+    if t.dim() != 4 or t.stride(1) != 1:
+        raise RuntimeError("expected a channels_last (B,C,H,W) tensor")
+    return t.stride(0), t.stride(2), t.stride(3)
+
+
+def upsample2x_cat(a, b=None):
+    """Bilinear x2 (align_corners=True) of cat([a, b], 1) for channels_last (B,C,H,W) inputs.
+    Returns a channels_last (B, Ca+Cb, 2H, 2W) tensor (a permuted view of NHWC storage)."""
+    _need_cuda(a, b)
+    B, Ca, H, W = a.shape
+    Cb = 0 if b is None else b.shape[1]
+    if b is not None and (b.shape[0] != B or b.shape[2:] != a.shape[2:] or b.dtype != a.dtype):
+        raise RuntimeError("upsample2x_cat: sources disagree in shape or dtype")
+    out = torch.empty((B, 2 * H, 2 * W, Ca + Cb), dtype=a.dtype, device=a.device)
+    sa = _nhwc_strides(a)
+    sb = (0, 0, 0) if b is None else _nhwc_strides(b)
+    check(lib.cp_upsample2x_cat_nhwc(_p(a), sa[0], sa[1], sa[2], Ca, _p(b), sb[0], sb[1], sb[2], Cb, _dt(a), _p(out),
+                                     B, H, W, _stream()), "cp_upsample2x_cat_nhwc")
+    _count()
+    return out.permute(0, 3, 1, 2)
+
+
 # ------------------------------------------------------------------------------- tcgen05 chain
 class _Layer(ChainLayer):
     """ChainLayer that keeps its tensors alive until the launch has been issued."""

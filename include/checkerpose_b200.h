@@ -136,6 +136,14 @@ int cp_chain_fwd(const cp_chain_params* p, cp_stream_t s);
 int cp_sample_taps(const void* patches, int dtype, int Hp, int Wp, int E, int tap_step, const int64_t* x_id,
                    const int64_t* y_id, const float* mask, void* out, int B, int N, cp_stream_t s);
 
+/* ---- image branch glue (pipeline.py:372-373 + nn.UpsamplingBilinear2d of pipeline.py:201) -------
+ * out (B, 2H, 2W, Ca+Cb) NHWC = bilinear x2 upsampling (align_corners=True) of cat([a, b], channel).
+ * a, b are NHWC views: channel stride 1, element strides (sb, sh, sw) given; Cb may be 0 (b NULL).
+ * Channels and strides must be multiples of 16 bytes.  The convolutions around it stay on cuDNN. */
+int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_sw, int Ca, const void* b,
+                           int64_t b_sb, int64_t b_sh, int64_t b_sw, int Cb, int dtype, void* out, int B,
+                           int H, int W, cp_stream_t s);
+
 /* ---- K4: sign-bit decode ------------------------------------------------------------------------
  * Init stage (pipeline.py:363-369): logits (B*N, ld) f32 rows = [roi, x_0..x_{L-1}, y_0..y_{L-1}].
  * Writes roi_bit (B,1,N), planes 0..L-1 of x_bits / y_bits (B, Ltot, N), roi_mask (B,N) f32 {0,1} and

@@ -329,3 +329,20 @@ def test_chain_agg_prologue(cp):
     # the SIMT aggregation kernel computes the same thing
     y = ops.edge_aggregate(z.cuda().to(torch.bfloat16), idx.cuda(), sel.cuda(), 0.2)
     assert torch.equal(y.cpu().float(), a_bf)
+
+
+# ------------------------------------------------------------------------------------------------ image branch glue
+@pytest.mark.parametrize("dtype,Ca,Cb,H", [(torch.float32, 8, 4, 5), (torch.bfloat16, 256, 512, 16), (torch.bfloat16, 64, 0, 7)])
+def test_upsample2x_cat(cp, dtype, Ca, Cb, H):
+    """cp_upsample2x_cat_nhwc == UpsamplingBilinear2d(scale_factor=2)(cat([a, b], 1)) (pipeline.py:201, 372)."""
+    g = torch.Generator().manual_seed(11)
+    B, W = 3, H + 2
+    a = torch.randn(B, Ca, H, W, generator=g).to(dtype)
+    b = torch.randn(B, Cb, H, W, generator=g).to(dtype) if Cb else None
+    cl = torch.channels_last
+    out = cp.ops.upsample2x_cat(a.cuda().contiguous(memory_format=cl), None if b is None else b.cuda().contiguous(memory_format=cl))
+    src = a if b is None else torch.cat([a, b], 1)
+    ref = torch.nn.UpsamplingBilinear2d(scale_factor=2)(src.float())
+    assert out.shape == ref.shape and out.dtype == dtype
+    tol = 1e-6 if dtype == torch.float32 else 8e-3   # bf16: one rounding of the output
+    assert torch.allclose(out.float().cpu(), ref, rtol=tol, atol=tol)

@@ -32,6 +32,22 @@ class ChainParams(C.Structure):
     ]
 
 
+class GraphPlanStruct(C.Structure):
+    _fields_ = [("G", c_i32), ("N", c_i32), ("K", c_i32), ("KP", c_i32), ("T", c_i32), ("umax", c_i32),
+                ("ucount", c_vp), ("ulist", c_vp), ("lidx", c_vp)]
+
+
+class EdgeConvParams(C.Structure):
+    _fields_ = [
+        ("B", c_i32), ("N", c_i32),
+        ("z", c_vp), ("ld_z", c_i32), ("Co", c_i32),
+        ("plan", GraphPlanStruct), ("graph_sel", c_vp), ("agg_slope", c_f32),
+        ("a_out", c_vp), ("ld_a_out", c_i32),
+        ("layer", ChainLayer),
+        ("out_mode", c_i32), ("out", c_vp), ("ld_out", c_i32), ("n_valid", c_i32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol of include/checkerpose_b200.h
 SIGNATURES = {
     "cp_last_error_string": (C.c_char_p, []),
@@ -51,8 +67,11 @@ SIGNATURES = {
     "cp_sample_taps": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     "cp_upsample2x_cat_nhwc": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32,
                                        c_i32, c_i32, c_vp]),
-    "cp_decode_init": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
-    "cp_decode_refine": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "cp_decode_init": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "cp_decode_refine": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "cp_permute_rows": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    "cp_graph_plan_build": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cp_edgeconv_fwd": (c_i32, [C.POINTER(EdgeConvParams), c_vp]),
     "cp_correspondences": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cp_threshold": (c_i32, [c_vp, c_f32, c_i32, c_vp, c_i32, c_i64, c_vp]),
     "cp_id_to_bits": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),

@@ -1,0 +1,450 @@
+// K2: staged, warp-specialised EdgeConv kernel (bf16 operands, fp32 accumulation in TMEM).
+//
+// Replaces StaticGraph_module.forward of checkerpose/model/pipeline.py:45-59 (get_graph_feature :27-40 +
+// Conv2d 1x1 + BatchNorm2d + LeakyReLU + max over K) in the factored form of cp_fold_edgeconv, fused with
+// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 16 warps per SM:
+//
+//   warp 2      stage producer: for every 64-channel slice of a 128-node tile it copies the tile's DISTINCT
+//               neighbour rows (plan.ulist, ~240 rows x 128 B instead of 128 x K gathered rows) from the [P|Q]
+//               table into a shared-memory staging buffer with cp.async.bulk (TMA engine), two buffers deep,
+//               and the tile's local neighbour indices (plan.lidx) once per tile;
+//   warps 8-15  aggregators: quarter-warps own nodes; each takes max_k over its staged neighbour rows with
+//               128-bit shared-memory loads, adds the node's own Q slice, applies LeakyReLU and writes the
+//               bf16 A operand slice straight into the SWIZZLE_128B layout tcgen05.mma reads;
+//   warp 1      weight producer: streams the packed weight tiles (16 KB) through a 3-stage ring;
+//   warp 0      one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete;
+//   warps 4-7   epilogue: TMEM -> registers -> bias / LeakyReLU -> bf16 (or fp32 logits) -> global.
+//
+// The aggregation of tile i+1 overlaps the MMAs and the epilogue of tile i; every hand-off is an mbarrier.
+// Per tile the SM moves ~1.3 MB through shared-memory loads (128 x K x 512 B), which is the kernel's
+// bound; L2 -> SM traffic drops from 128 x K gathered rows to the distinct rows.
+#include "common.cuh"
+#include "sm100.cuh"
+
+using bf16 = __nv_bfloat16;
+using namespace sm100;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NTHREADS = 512;
+constexpr int AGG_WARP0 = 8, NUM_AGG_WARPS = 8;
+constexpr int EPI_WARP0 = 4;
+constexpr int A_CHUNK_BYTES = TILE_M * 128;  // 128 rows x 64 bf16
+constexpr int A_CHUNKS = 4;
+constexpr int B_STAGE_BYTES = 128 * 128;
+constexpr int B_STAGES = 3;
+constexpr int UMAX = CP_PLAN_UMAX;
+constexpr int STG_BYTES = UMAX * 128;
+constexpr int KP_MAX = 40;
+constexpr int LIDX_BYTES = TILE_M * KP_MAX * 2;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_WTILES = 16;
+
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + A_CHUNKS * A_CHUNK_BYTES;
+constexpr int OFF_STG = OFF_B + B_STAGES * B_STAGE_BYTES;
+constexpr int OFF_LIDX = OFF_STG + 2 * STG_BYTES;
+constexpr int OFF_BAR = OFF_LIDX + 2 * LIDX_BYTES;
+constexpr int SMEM_BYTES = 1024 + OFF_BAR + 256;
+
+struct WTile {
+  const uint8_t* ptr;
+  uint32_t bytes;  // rows * 128
+  uint32_t pad;
+};
+
+struct EcParams {
+  cp_edgeconv_params p;
+  int KC;            // 64-channel slices of the aggregated feature (= GEMM K chunks)
+  int NB;            // 128-column blocks of the GEMM output
+  int npad;          // nout rounded up to 16
+  int num_tiles;     // B * plan.T
+  WTile wt[MAX_WTILES];  // order: slice-major, then column block
+};
+
+struct Bars {
+  uint64_t stg_full[2], stg_empty[2];
+  uint64_t a_full[A_CHUNKS], a_empty[A_CHUNKS];
+  uint64_t b_full[B_STAGES], b_empty[B_STAGES];
+  uint64_t acc_full, acc_empty;
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ uint32_t a_offset(int kc, int row, int chunk) {
+  return (uint32_t)(OFF_A + kc * A_CHUNK_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint4 bf8_max(uint4 a, uint4 b) {
+  return make_uint4(bf2_max(a.x, b.x), bf2_max(a.y, b.y), bf2_max(a.z, b.z), bf2_max(a.w, b.w));
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t a) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&a)); }
+__device__ __forceinline__ uint32_t f2_to_bf2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// role bodies
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_coords(const EcParams& kp, int tile, int& b, int& t, int& g) {
+  b = tile / kp.p.plan.T;
+  t = tile - b * kp.p.plan.T;
+  g = kp.p.graph_sel ? __ldg(kp.p.graph_sel + b) : 0;
+}
+
+__device__ void stage_producer(const EcParams& kp, uint8_t* sm, Bars* bars, int lane) {
+  const cp_edgeconv_params& p = kp.p;
+  const cp_graph_plan& pl = p.plan;
+  const uint32_t row_bytes = (uint32_t)p.ld_z * 2;
+  uint32_t it = 0;  // staging rounds issued
+  int ti = 0;
+  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
+    int b, t, g;
+    tile_coords(kp, tile, b, t, g);
+    const int U = __ldg(pl.ucount + (size_t)g * pl.T + t);
+    const int32_t* ul = pl.ulist + ((size_t)g * pl.T + t) * pl.umax;
+    const uint8_t* zb = reinterpret_cast<const uint8_t*>(p.z) + (size_t)b * p.N * row_bytes;
+    uint32_t src_off[UMAX / 32];  // byte offset of each of this lane's rows inside the RoI's table
+#pragma unroll
+    for (int q = 0; q < UMAX / 32; ++q) {
+      const int u = q * 32 + lane;
+      src_off[q] = (u < U) ? (uint32_t)__ldg(ul + u) * row_bytes : 0u;
+    }
+    const int rows_valid = min(TILE_M, p.N - t * TILE_M);
+    const uint32_t lidx_bytes = (uint32_t)rows_valid * pl.KP * 2;
+    for (int c = 0; c < kp.KC; ++c, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = it >> 1;
+      if (use > 0) mbar_wait(&bars->stg_empty[buf], (use - 1) & 1);
+      uint64_t* full = &bars->stg_full[buf];
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full, (uint32_t)U * 128u + (c == 0 ? lidx_bytes : 0u));
+        if (c == 0)
+          bulk_g2s(sm + OFF_LIDX + (ti & 1) * LIDX_BYTES, pl.lidx + ((size_t)g * pl.N + (size_t)t * TILE_M) * pl.KP, lidx_bytes, full);
+      }
+      uint8_t* dst = sm + OFF_STG + buf * STG_BYTES;
+      const uint8_t* src = zb + c * 128;
+#pragma unroll
+      for (int q = 0; q < UMAX / 32; ++q) {
+        const int u = q * 32 + lane;
+        if (u < U) bulk_g2s(dst + u * 128, src + src_off[q], 128, full);
+      }
+    }
+  }
+}
+
+__device__ void weight_producer(const EcParams& kp, uint8_t* sm, Bars* bars) {
+  const int T = kp.KC * kp.NB;
+  uint32_t cnt = 0;
+  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x) {
+    for (int w = 0; w < T; ++w, ++cnt) {
+      const int s = cnt % B_STAGES;
+      const uint32_t use = cnt / B_STAGES;
+      if (use > 0) mbar_wait(&bars->b_empty[s], (use - 1) & 1);
+      mbar_arrive_expect_tx(&bars->b_full[s], kp.wt[w].bytes);
+      bulk_g2s(sm + OFF_B + s * B_STAGE_BYTES, kp.wt[w].ptr, kp.wt[w].bytes, &bars->b_full[s]);
+    }
+  }
+}
+
+__device__ void mma_issuer(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base) {
+  uint32_t cnt = 0;
+  int ti = 0;
+  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
+    if (ti > 0) {
+      mbar_wait(&bars->acc_empty, (ti - 1) & 1);  // epilogue of the previous tile has drained TMEM
+      tc_fence_after_sync();
+    }
+    for (int c = 0; c < kp.KC; ++c) {
+      mbar_wait(&bars->a_full[c], ti & 1);
+      tc_fence_after_sync();
+      const uint32_t a_addr = smem_u32(sm + OFF_A + c * A_CHUNK_BYTES);
+      for (int nb = 0; nb < kp.NB; ++nb, ++cnt) {
+        const int s = cnt % B_STAGES;
+        mbar_wait(&bars->b_full[s], (cnt / B_STAGES) & 1);
+        tc_fence_after_sync();
+        const uint32_t b_addr = smem_u32(sm + OFF_B + s * B_STAGE_BYTES);
+        const uint32_t idesc = make_idesc_bf16_m128(kp.wt[c * kp.NB + nb].bytes >> 7);
+        const uint32_t d = tmem_base + (uint32_t)(nb * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((c | k) != 0));
+        mma_commit(&bars->b_empty[s]);
+      }
+      mma_commit(&bars->a_empty[c]);
+    }
+    mma_commit(&bars->acc_full);
+  }
+}
+
+__device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, int lane) {
+  const cp_edgeconv_params& p = kp.p;
+  const int KP = p.plan.KP, K = p.plan.K;
+  const int lg = lane >> 3, sub = lane & 7;
+  const int gid = aw * 4 + lg;  // quarter-warp id, 0..31: owns rows 4*gid .. 4*gid+3 of the tile
+  const uint32_t sm_base = smem_u32(sm);
+  const float slope = p.agg_slope;
+  uint32_t it = 0;
+  int ti = 0;
+  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
+    int b, t, g;
+    tile_coords(kp, tile, b, t, g);
+    const int n0 = t * TILE_M;
+    const int rows_valid = min(TILE_M, p.N - n0);
+    const size_t row0 = (size_t)b * p.N + n0;
+    const bf16* zq = reinterpret_cast<const bf16*>(p.z) + row0 * p.ld_z + p.Co + sub * 8;  // own Q slices
+    bf16* aout = p.a_out ? reinterpret_cast<bf16*>(p.a_out) + row0 * p.ld_a_out + sub * 8 : nullptr;
+    const uint32_t lidx_s = sm_base + OFF_LIDX + (ti & 1) * LIDX_BYTES;
+    for (int c = 0; c < kp.KC; ++c, ++it) {
+      const int buf = it & 1;
+      // own Q slices first: their latency hides behind the barrier waits
+      uint4 q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = gid * 4 + j;
+        q[j] = (r < rows_valid) ? ldg_nc_v4(zq + (size_t)r * p.ld_z + c * 64) : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&bars->stg_full[buf], (it >> 1) & 1);
+      if (ti > 0) mbar_wait(&bars->a_empty[c], (ti - 1) & 1);
+      const uint32_t stg = sm_base + OFF_STG + buf * STG_BYTES + sub * 16;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = gid * 4 + j;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (r < rows_valid) {
+          const uint32_t li = lidx_s + (uint32_t)(r * KP) * 2;
+          uint4 m = make_uint4(0, 0, 0, 0);
+          for (int k0 = 0; k0 < K; k0 += 8) {
+            const uint4 iv = lds128(li + k0 * 2);  // 8 local indices (broadcast within the quarter-warp)
+            const uint32_t w[4] = {iv.x, iv.y, iv.z, iv.w};
+            uint4 mm;
+            if (K - k0 >= 8) {
+              uint4 v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t l = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+                v[e] = lds128(stg + l * 128);
+              }
+              mm = bf8_max(bf8_max(bf8_max(v[0], v[1]), bf8_max(v[2], v[3])), bf8_max(bf8_max(v[4], v[5]), bf8_max(v[6], v[7])));
+            } else {  // tail of the neighbour list (warp-uniform trip count)
+              mm = lds128(stg + (w[0] & 0xffffu) * 128);
+#pragma unroll
+              for (int e = 1; e < 8; ++e) {
+                if (e < K - k0) {
+                  const uint32_t l = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+                  mm = bf8_max(mm, lds128(stg + l * 128));
+                }
+              }
+            }
+            m = (k0 == 0) ? mm : bf8_max(m, mm);
+          }
+          const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, qw[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = bf2_to_f2(mw[e]), d = bf2_to_f2(qw[e]);
+            ow[e] = f2_to_bf2(cp::lrelu(a.x + d.x, slope), cp::lrelu(a.y + d.y, slope));
+          }
+          o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          if (aout) *reinterpret_cast<uint4*>(aout + (size_t)r * p.ld_a_out + c * 64) = o;
+        }
+        sts128(sm_base + a_offset(c, r, sub), o);
+      }
+      fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->a_full[c]);
+        mbar_arrive(&bars->stg_empty[buf]);
+      }
+    }
+  }
+}
+
+__device__ void epilogue_warps(const EcParams& kp, Bars* bars, uint32_t tmem_base, int q, int lane) {
+  const cp_edgeconv_params& p = kp.p;
+  const cp_chain_layer& L = p.layer;
+  const int row = q * 32 + lane;
+  const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+  int ti = 0;
+  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
+    const int b = tile / p.plan.T, t = tile - b * p.plan.T;
+    const int n0 = t * TILE_M;
+    const bool row_ok = row < min(TILE_M, p.N - n0);
+    const size_t grow = (size_t)b * p.N + n0 + row;
+    mbar_wait(&bars->acc_full, ti & 1);
+    tc_fence_after_sync();
+    for (int c0 = 0; c0 < kp.npad; c0 += 32) {
+      uint32_t r[32];
+      if (kp.npad - c0 >= 32) {
+        tmem_ld32(tbase + (uint32_t)c0, r);
+      } else {  // npad is a multiple of 16
+        uint32_t h[16];
+        tmem_ld16(tbase + (uint32_t)c0, h);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { r[e] = h[e]; r[16 + e] = 0; }
+      }
+      tmem_ld_wait();
+      const int ncols = min(32, kp.npad - c0);
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        float x = __uint_as_float(r[e]);
+        if (L.bias && c0 + e < L.nout) x += __ldg(L.bias + c0 + e);
+        if (L.act) x = cp::lrelu(x, L.slope);
+        v[e] = x;
+      }
+      if (!row_ok) continue;
+      if (p.out_mode == CP_OUT_BF16) {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ld_out + c0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (e * 8 < ncols)
+            *reinterpret_cast<uint4*>(o + e * 8) = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
+                                                              f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + grow * p.ld_out;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c0 + e < p.n_valid) o[c0 + e] = v[e];
+      }
+    }
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars->acc_empty);
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_constant__ EcParams kp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->stg_full[s], 1);
+      mbar_init(&bars->stg_empty[s], NUM_AGG_WARPS);
+    }
+    for (int c = 0; c < A_CHUNKS; ++c) {
+      mbar_init(&bars->a_full[c], NUM_AGG_WARPS);
+      mbar_init(&bars->a_empty[c], 1);
+    }
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(&bars->b_full[s], 1);
+      mbar_init(&bars->b_empty[s], 1);
+    }
+    mbar_init(&bars->acc_full, 1);
+    mbar_init(&bars->acc_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) mma_issuer(kp, sm, bars, tmem_base);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) weight_producer(kp, sm, bars);
+    __syncwarp();
+  } else if (warp == 2) {
+    stage_producer(kp, sm, bars, lane);
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+    epilogue_warps(kp, bars, tmem_base, warp - EPI_WARP0, lane);
+  } else if (warp >= AGG_WARP0) {
+    aggregator(kp, sm, bars, warp - AGG_WARP0, lane);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace
+
+extern "C" int cp_edgeconv_fwd(const cp_edgeconv_params* pp, cp_stream_t s) {
+  CP_REQUIRE(pp, CP_E_INVALID, "cp_edgeconv_fwd: null params");
+  const cp_edgeconv_params& p = *pp;
+  const cp_graph_plan& pl = p.plan;
+  const cp_chain_layer& L = p.layer;
+  CP_REQUIRE(p.B > 0 && p.N > 0 && p.z && p.out, CP_E_INVALID, "cp_edgeconv_fwd: bad B=%d N=%d or null tensor", p.B, p.N);
+  CP_REQUIRE(p.Co == 64 || p.Co == 128 || p.Co == 256, CP_E_UNSUPPORTED, "cp_edgeconv_fwd: Co=%d not in {64,128,256}", p.Co);
+  CP_REQUIRE(p.ld_z >= 2 * p.Co && (p.ld_z % 8) == 0 && (reinterpret_cast<uintptr_t>(p.z) & 15) == 0, CP_E_INVALID,
+             "cp_edgeconv_fwd: z must be 16-byte aligned with ld_z %% 8 == 0 and ld_z >= 2*Co (ld_z=%d)", p.ld_z);
+  CP_REQUIRE(pl.ucount && pl.ulist && pl.lidx && pl.N == p.N && pl.T == (p.N + TILE_M - 1) / TILE_M && pl.G >= 1, CP_E_INVALID,
+             "cp_edgeconv_fwd: graph plan does not match N=%d", p.N);
+  CP_REQUIRE(pl.K >= 1 && pl.KP == (pl.K + 7) / 8 * 8 && pl.KP <= KP_MAX, CP_E_UNSUPPORTED, "cp_edgeconv_fwd: K=%d outside [1,%d]", pl.K, KP_MAX);
+  CP_REQUIRE(pl.umax == UMAX, CP_E_INVALID, "cp_edgeconv_fwd: plan.umax=%d, expected %d", pl.umax, UMAX);
+  CP_REQUIRE((reinterpret_cast<uintptr_t>(pl.lidx) & 15) == 0, CP_E_INVALID, "cp_edgeconv_fwd: plan.lidx must be 16-byte aligned");
+  CP_REQUIRE(!p.a_out || (p.ld_a_out >= p.Co && (p.ld_a_out % 8) == 0), CP_E_INVALID, "cp_edgeconv_fwd: bad ld_a_out");
+  CP_REQUIRE(L.w_packed && L.kin == p.Co && L.nout >= 1, CP_E_INVALID, "cp_edgeconv_fwd: layer kin=%d must equal Co=%d", L.kin, p.Co);
+  CP_REQUIRE((reinterpret_cast<uintptr_t>(L.w_packed) & 15) == 0, CP_E_INVALID, "cp_edgeconv_fwd: weights not 16-byte aligned");
+  EcParams kp;
+  kp.p = p;
+  kp.KC = p.Co / 64;
+  kp.npad = (L.nout + 15) & ~15;
+  CP_REQUIRE(kp.npad <= TMEM_COLS, CP_E_UNSUPPORTED, "cp_edgeconv_fwd: nout=%d > 512", L.nout);
+  kp.NB = (kp.npad + 127) / 128;
+  kp.num_tiles = p.B * pl.T;
+  if (p.out_mode == CP_OUT_BF16)
+    CP_REQUIRE((p.ld_out % 8) == 0 && p.ld_out >= kp.npad, CP_E_INVALID, "cp_edgeconv_fwd: bf16 output needs ld_out %% 8 == 0 and >= %d", kp.npad);
+  else
+    CP_REQUIRE(p.out_mode == CP_OUT_F32 && p.n_valid >= 1 && p.n_valid <= p.ld_out && p.n_valid <= kp.npad, CP_E_INVALID,
+               "cp_edgeconv_fwd: bad f32 output spec");
+  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(L.w_packed);
+  for (int c = 0; c < kp.KC; ++c)
+    for (int nb = 0; nb < kp.NB; ++nb) {
+      const int rows = (kp.npad - nb * 128 < 128) ? (kp.npad - nb * 128) : 128;
+      WTile& w = kp.wt[c * kp.NB + nb];
+      w.ptr = wbase + (size_t)nb * 128 * L.kin * 2 + (size_t)c * rows * 128;
+      w.bytes = (uint32_t)rows * 128;
+      w.pad = 0;
+    }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
+  cudaError_t e = cudaFuncSetAttribute(edgeconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  CP_REQUIRE(e == cudaSuccess, CP_E_CUDA, "cp_edgeconv_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  edgeconv_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)s>>>(kp);
+  CP_CHECK_LAUNCH("cp_edgeconv_fwd");
+  return CP_OK;
+}

@@ -233,21 +233,31 @@ sample_taps_kernel(const T* __restrict__ patches, int Hp, int Wp, int E, int ste
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
+// Node-major tensors inside the head are in PLAN order (cp_graph_plan_build); the reference's outputs are in
+// keypoint order.  perm (G,N): plan position -> keypoint id; NULL = identity.
+__device__ __forceinline__ int plan_to_keypoint(const int32_t* perm, const int32_t* graph_sel, int b, int n, int N) {
+  if (!perm) return n;
+  const int g = graph_sel ? graph_sel[b] : 0;
+  return perm[(size_t)g * N + n];
+}
+
 __global__ void decode_init_kernel(const float* __restrict__ logits, int ld, int L, int Ltot, float* __restrict__ roi_bit,
                                    float* __restrict__ x_bits, float* __restrict__ y_bits, float* __restrict__ roi_mask,
-                                   int64_t* __restrict__ x_id, int64_t* __restrict__ y_id, int B, int N) {
+                                   int64_t* __restrict__ x_id, int64_t* __restrict__ y_id, int B, int N,
+                                   const int32_t* __restrict__ perm, const int32_t* __restrict__ graph_sel) {
   const int64_t total = (int64_t)B * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(e / N), n = (int)(e - (int64_t)b * N);
+    const int kp = plan_to_keypoint(perm, graph_sel, b, n, N);
     const float* row = logits + e * ld;
     const float r = row[0];
-    roi_bit[e] = r;
+    roi_bit[(size_t)b * N + kp] = r;
     if (roi_mask) roi_mask[e] = r > 0.f ? 1.f : 0.f;
     int64_t xi = 0, yi = 0;
     for (int l = 0; l < L; ++l) {
       const float xv = row[1 + l], yv = row[1 + L + l];
-      x_bits[((size_t)b * Ltot + l) * N + n] = xv;
-      y_bits[((size_t)b * Ltot + l) * N + n] = yv;
+      x_bits[((size_t)b * Ltot + l) * N + kp] = xv;
+      y_bits[((size_t)b * Ltot + l) * N + kp] = yv;
       xi = xi * 2 + (xv > 0.f ? 1 : 0);
       yi = yi * 2 + (yv > 0.f ? 1 : 0);
     }
@@ -258,15 +268,33 @@ __global__ void decode_init_kernel(const float* __restrict__ logits, int ld, int
 
 __global__ void decode_refine_kernel(const float* __restrict__ logits, int ld, int plane, int Ltot,
                                      float* __restrict__ x_bits, float* __restrict__ y_bits, int64_t* __restrict__ x_id,
-                                     int64_t* __restrict__ y_id, int B, int N) {
+                                     int64_t* __restrict__ y_id, int B, int N, const int32_t* __restrict__ perm,
+                                     const int32_t* __restrict__ graph_sel) {
   const int64_t total = (int64_t)B * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(e / N), n = (int)(e - (int64_t)b * N);
+    const int kp = plan_to_keypoint(perm, graph_sel, b, n, N);
     const float xv = logits[e * ld], yv = logits[e * ld + 1];
-    x_bits[((size_t)b * Ltot + plane) * N + n] = xv;
-    y_bits[((size_t)b * Ltot + plane) * N + n] = yv;
+    x_bits[((size_t)b * Ltot + plane) * N + kp] = xv;
+    y_bits[((size_t)b * Ltot + plane) * N + kp] = yv;
     x_id[e] = x_id[e] * 2 + (xv > 0.f ? 1 : 0);
     y_id[e] = y_id[e] * 2 + (yv > 0.f ? 1 : 0);
+  }
+}
+
+// dst[b, perm[n], :] = src[b, n, :] (to_keypoint_order != 0) or dst[b, n, :] = src[b, perm[n], :] (== 0); rows of
+// `row_bytes` bytes (multiple of 4) moved as 32-bit words, one warp per row.
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int words, int B, int N,
+                    const int32_t* __restrict__ perm, const int32_t* __restrict__ graph_sel, int to_keypoint_order) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)B * N;
+  for (int64_t e = (int64_t)blockIdx.x * 8 + warp; e < total; e += (int64_t)gridDim.x * 8) {
+    const int b = (int)(e / N), n = (int)(e - (int64_t)b * N);
+    const int kp = plan_to_keypoint(perm, graph_sel, b, n, N);
+    const int64_t s = to_keypoint_order ? e : (int64_t)b * N + kp;
+    const int64_t d = to_keypoint_order ? (int64_t)b * N + kp : e;
+    for (int w = lane; w < words; w += 32) dst[d * words + w] = src[s * words + w];
   }
 }
 
@@ -468,23 +496,36 @@ int cp_sample_taps(const void* patches, int dtype, int Hp, int Wp, int E, int ta
 }
 
 int cp_decode_init(const float* logits, int ld, int L, int Ltot, float* roi_bit, float* x_bits, float* y_bits,
-                   float* roi_mask, int64_t* x_id, int64_t* y_id, int B, int N, cp_stream_t s) {
+                   float* roi_mask, int64_t* x_id, int64_t* y_id, int B, int N, const int32_t* perm,
+                   const int32_t* graph_sel, cp_stream_t s) {
   CP_REQUIRE(logits && roi_bit && x_bits && y_bits && x_id && y_id && B > 0 && N > 0, CP_E_INVALID,
              "cp_decode_init: bad arguments");
   CP_REQUIRE(L >= 1 && L <= Ltot && ld >= 1 + 2 * L, CP_E_INVALID, "cp_decode_init: bad L=%d Ltot=%d ld=%d", L, Ltot, ld);
   decode_init_kernel<<<grid_for((int64_t)B * N), 256, 0, (cudaStream_t)s>>>(logits, ld, L, Ltot, roi_bit, x_bits, y_bits,
-                                                                            roi_mask, x_id, y_id, B, N);
+                                                                            roi_mask, x_id, y_id, B, N, perm, graph_sel);
   CP_CHECK_LAUNCH("cp_decode_init");
   return CP_OK;
 }
 
 int cp_decode_refine(const float* logits, int ld, int plane, int Ltot, float* x_bits, float* y_bits, int64_t* x_id,
-                     int64_t* y_id, int B, int N, cp_stream_t s) {
+                     int64_t* y_id, int B, int N, const int32_t* perm, const int32_t* graph_sel, cp_stream_t s) {
   CP_REQUIRE(logits && x_bits && y_bits && x_id && y_id && B > 0 && N > 0, CP_E_INVALID, "cp_decode_refine: bad arguments");
   CP_REQUIRE(plane >= 0 && plane < Ltot && ld >= 2, CP_E_INVALID, "cp_decode_refine: bad plane=%d Ltot=%d ld=%d", plane, Ltot, ld);
   decode_refine_kernel<<<grid_for((int64_t)B * N), 256, 0, (cudaStream_t)s>>>(logits, ld, plane, Ltot, x_bits, y_bits, x_id,
-                                                                              y_id, B, N);
+                                                                              y_id, B, N, perm, graph_sel);
   CP_CHECK_LAUNCH("cp_decode_refine");
+  return CP_OK;
+}
+
+int cp_permute_rows(const void* src, void* dst, int row_bytes, int B, int N, const int32_t* perm, const int32_t* graph_sel,
+                    int to_keypoint_order, cp_stream_t s) {
+  CP_REQUIRE(src && dst && perm && B > 0 && N > 0 && row_bytes > 0 && (row_bytes % 4) == 0 && src != dst, CP_E_INVALID,
+             "cp_permute_rows: bad arguments (row_bytes=%d must be a multiple of 4, out of place)", row_bytes);
+  int64_t g = ((int64_t)B * N + 7) / 8;
+  if (g > 148 * 16) g = 148 * 16;
+  permute_rows_kernel<<<(int)g, 256, 0, (cudaStream_t)s>>>((const uint32_t*)src, (uint32_t*)dst, row_bytes / 4, B, N, perm,
+                                                           graph_sel, to_keypoint_order);
+  CP_CHECK_LAUNCH("cp_permute_rows");
   return CP_OK;
 }
 

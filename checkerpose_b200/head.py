@@ -128,18 +128,56 @@ class GraphTable:
         return hit[1]
 
 
-def graph_select(knn_idx: torch.Tensor, obj_ids, batch: int, device):
-    """-> (idx32 (G,N,K), graph_sel int32 (B) or None).  LM nets index with 1-based ids (pipeline_lm.py:56-57)."""
-    if hasattr(knn_idx, "get"):       # LazyKnnGraph
-        knn_idx = knn_idx.get(device)
-    idx32 = GraphTable.get(knn_idx, device)
+def _graph_tensor(knn_src, device):
+    return knn_src.get(device) if hasattr(knn_src, "get") else knn_src
+
+
+def graph_select(knn_idx, obj_ids, batch: int, device):
+    """-> (idx32 (G,N,K) in keypoint numbering, graph_sel int32 (B) or None).  LM nets index with 1-based ids
+    (pipeline_lm.py:56-57)."""
+    idx32 = GraphTable.get(_graph_tensor(knn_idx, device), device)
+    return idx32, _graph_sel(idx32.shape[0], obj_ids, batch, device)
+
+
+def _graph_sel(G, obj_ids, batch, device):
     if obj_ids is not None:
-        return idx32, (obj_ids.to(device=device, dtype=torch.int64) - 1).to(torch.int32).contiguous()
-    if idx32.shape[0] == 1:
-        return idx32, None
-    if idx32.shape[0] != batch:
-        raise RuntimeError(f"knn_idx has {idx32.shape[0]} graphs for a batch of {batch}")
-    return idx32, torch.arange(batch, dtype=torch.int32, device=device)
+        return (obj_ids.to(device=device, dtype=torch.int64) - 1).to(torch.int32).contiguous()
+    if G == 1:
+        return None
+    if G != batch:
+        raise RuntimeError(f"knn_idx has {G} graphs for a batch of {batch}")
+    return torch.arange(batch, dtype=torch.int32, device=device)
+
+
+class GraphCtx:
+    """What the kernels need to know about a module's static graph for one batch: the plan (keypoint renumbering,
+    plan-order neighbour table, staging lists) and the per-RoI graph selector."""
+
+    __slots__ = ("plan", "sel")
+
+    def __init__(self, plan, sel):
+        self.plan, self.sel = plan, sel
+
+    def to_plan(self, x_nm):
+        """(B,N,...) keypoint order -> plan order."""
+        return x_nm if self.plan.identity else ops.permute_rows(x_nm, self.plan.perm, self.sel, False)
+
+    def to_keypoints(self, x_nm):
+        """(B,N,...) plan order -> keypoint order."""
+        return x_nm if self.plan.identity else ops.permute_rows(x_nm, self.plan.perm, self.sel, True)
+
+
+def graph_ctx(knn_src, obj_ids, batch: int, device) -> GraphCtx:
+    """Plan of a module's graph (built once, cached on the graph object) + selector for this batch."""
+    device = torch.device(device)
+    t = _graph_tensor(knn_src, device)
+    hit = getattr(t, "_cp_plan", None)
+    if hit is None or hit[0] != t._version or hit[1].perm.device != device:
+        xyz = getattr(knn_src, "p3d_normed", None)
+        hit = (t._version, ops.GraphPlan(GraphTable.get(t, device), xyz))
+        t._cp_plan = hit
+    plan = hit[1]
+    return GraphCtx(plan, _graph_sel(plan.G, obj_ids, batch, device))
 
 
 def _require_eval(module):
@@ -153,29 +191,40 @@ def _chain_ok(C):
 
 
 # --------------------------------------------------------------------------------------------------
-# EdgeConv (K2)
+# EdgeConv (K2).  Every node-major tensor below is in PLAN order (GraphCtx.to_plan / to_keypoints convert).
 # --------------------------------------------------------------------------------------------------
-def edgeconv_node_major(sg_module, x_nm, idx32, graph_sel, dtype):
-    """x_nm (B,N,C) of ``dtype`` -> (B,N,Co).  StaticGraph_module.forward (pipeline.py:55-59)."""
+def _agg_gemm(z, ctx: GraphCtx, agg_slope, layer, out, out_mode, n_valid=0, a_out=None):
+    """A = EdgeConv aggregation of the [P|Q] table z; out = layer(A).  Staged warp-specialised kernel when the
+    graph plan fits it, else the unstaged chain kernel with direct global gathers."""
+    if ctx.plan.staged:
+        return ops.edgeconv_fwd(z=z, plan=ctx.plan, graph_sel=ctx.sel, agg_slope=agg_slope, layer=layer, out=out,
+                                out_mode=out_mode, n_valid=n_valid, a_out=a_out)
+    return ops.chain_fwd(prologue=ops.PRO_AGG, B=z.shape[0], N=z.shape[1], z=z, idx32=ctx.plan.idx_p, graph_sel=ctx.sel,
+                         agg_slope=agg_slope, a_out=a_out, layers=[layer], out=out, out_mode=out_mode, n_valid=n_valid)
+
+
+def edgeconv_node_major(sg_module, x_nm, ctx: GraphCtx, dtype):
+    """x_nm (B,N,C) of ``dtype`` -> (B,N,Co).  StaticGraph_module.forward (pipeline.py:55-59), one layer on its own."""
     _require_eval(sg_module)
     prep = prepared_edgeconv(sg_module, dtype)
     B, N, C = x_nm.shape
     if dtype == torch.float32:
         z = ops.linear_f32(x_nm, prep.w, prep.b)
-        return ops.edge_aggregate(z, idx32, graph_sel, prep.slope)
+        return ops.edge_aggregate(z, ctx.plan.idx_p, ctx.sel, prep.slope)
     if not (_chain_ok(C) and _chain_ok(prep.Co)):
         raise RuntimeError(f"bf16 EdgeConv supports C, C' in {{64,128,256}} (got {C}->{prep.Co}); use float32 mode")
     z = torch.empty((B, N, 2 * prep.Co), dtype=torch.bfloat16, device=x_nm.device)
     ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x_nm,
                   layers=[ops.chain_layer(prep.packed, prep.b, C, 2 * prep.Co, False, 0.0)], out=z, out_mode=ops.OUT_BF16)
-    return ops.edge_aggregate(z, idx32, graph_sel, prep.slope)
+    return ops.edge_aggregate(z, ctx.plan.idx_p, ctx.sel, prep.slope)
 
 
 # --------------------------------------------------------------------------------------------------
 # init head (InitNet_GNN.forward after the backbone, init.py:112-122)
 # --------------------------------------------------------------------------------------------------
 def init_head_node_major(init_net, feat_last, obj_ids, dtype):
-    """-> logits (B,N,7) f32, graph feature (B,N,64) of ``dtype``."""
+    """-> logits (B,N,>=7) f32, graph feature (B,N,64) of ``dtype`` (both in plan order), GraphCtx (None without
+    graph modules)."""
     _require_eval(init_net)
     B = feat_last.shape[0]
     N = init_net.npoint
@@ -188,22 +237,23 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
             x0 = init_net.conv1x1(feat_last.float())
     x = x0.contiguous().view(B, N, 64)  # == out.view(-1, N, 64): channel = 8x8 cell (init.py:114)
     blocks = list(init_net.pre_query_block)
-    idx32, sel = (None, None)
-    if blocks:
-        idx32, sel = graph_select(blocks[0]._knn, obj_ids, B, dev)
     mlp = prepared_linear(init_net.mlp, dtype)
     nbits = mlp.nout
+    ctx = None
+    if blocks:
+        ctx = graph_ctx(blocks[0]._knn, obj_ids, B, dev)
+        x = ctx.to_plan(x)
     if dtype == torch.float32:
         for blk in blocks:
-            x = edgeconv_node_major(blk, x, idx32, sel, dtype)
+            x = edgeconv_node_major(blk, x, ctx, dtype)
         logits = ops.linear_f32(x, mlp.w, mlp.b)
-        return logits, x
-    # bf16: LOAD->[Wcat_0] ; AGG->[Wcat_j] ... ; AGG(+store feature)->[mlp]
+        return logits, x, ctx
+    # bf16: LOAD->[W_0] ; AGG->[W_j] ... ; AGG(+store feature)->[mlp]
     logits = torch.empty((B, N, 16), dtype=torch.float32, device=dev)
     mlp_layer = ops.chain_layer(mlp.packed, mlp.b, 64, nbits, False, 0.0)
     if not blocks:
         ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x, layers=[mlp_layer], out=logits, out_mode=ops.OUT_F32, n_valid=nbits)
-        return logits, x
+        return logits, x, ctx
     preps = [prepared_edgeconv(b, dtype) for b in blocks]
     for b in blocks:
         _require_eval(b)
@@ -213,14 +263,12 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
                   out=z, out_mode=ops.OUT_BF16)
     for j in range(1, len(blocks)):
         z2 = torch.empty((B, N, 2 * preps[j].Co), dtype=torch.bfloat16, device=dev)
-        ops.chain_fwd(prologue=ops.PRO_AGG, B=B, N=N, z=z, idx32=idx32, graph_sel=sel, agg_slope=preps[j - 1].slope,
-                      layers=[ops.chain_layer(preps[j].packed, preps[j].b, preps[j].C, 2 * preps[j].Co, False, 0.0)],
-                      out=z2, out_mode=ops.OUT_BF16)
+        _agg_gemm(z, ctx, preps[j - 1].slope, ops.chain_layer(preps[j].packed, preps[j].b, preps[j].C, 2 * preps[j].Co, False, 0.0),
+                  z2, ops.OUT_BF16)
         z = z2
     gfeat = torch.empty((B, N, preps[-1].Co), dtype=torch.bfloat16, device=dev)
-    ops.chain_fwd(prologue=ops.PRO_AGG, B=B, N=N, z=z, idx32=idx32, graph_sel=sel, agg_slope=preps[-1].slope, a_out=gfeat,
-                  layers=[mlp_layer], out=logits, out_mode=ops.OUT_F32, n_valid=nbits)
-    return logits, gfeat
+    _agg_gemm(z, ctx, preps[-1].slope, mlp_layer, logits, ops.OUT_F32, n_valid=nbits, a_out=gfeat)
+    return logits, gfeat, ctx
 
 
 # --------------------------------------------------------------------------------------------------
@@ -334,8 +382,9 @@ def patches_nhwc(patch_generator, img_feat, dtype):
 # --------------------------------------------------------------------------------------------------
 # refine stage (Refine_moduleGNN.forward, pipeline.py:262-298)
 # --------------------------------------------------------------------------------------------------
-def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, obj_ids, dtype):
-    """gfeat_nm (B,N,Cg) of ``dtype``, roi_mask (B,N) f32 {0,1}, ids (B,N) int64.
+def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, ctx, dtype):
+    """One refine stage on plan-order node tensors: gfeat_nm (B,N,Cg) of ``dtype``, roi_mask (B,N) f32 {0,1}, ids (B,N)
+    int64, ctx = graph_ctx of the stage's graph (None when it has no graph modules).
     -> logits (B,N,>=2) f32 [x_new, y_new], graph feature (B,N,C) of ``dtype``."""
     _require_eval(ref)
     B, N, Cg = gfeat_nm.shape
@@ -348,9 +397,6 @@ def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, obj_ids, dt
     blocks = list(ref.pre_query_block)
     q = [prepared_linear(ref.query_block.mlps[i], dtype) for i in (0, 2, 4)]
     qslope = float(ref.query_block.mlps[1].negative_slope)
-    idx32, sel = (None, None)
-    if blocks:
-        idx32, sel = graph_select(blocks[0]._knn, obj_ids, B, dev)
     x_id = x_id.contiguous()
     y_id = y_id.contiguous()
     if dtype == torch.float32:
@@ -358,12 +404,12 @@ def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, obj_ids, dt
         h = ops.linear_f32(taps, pg0.w, pg0.b, True, slope, a2=gfeat_nm)
         h = ops.linear_f32(h, pg1.w, pg1.b, True, slope)
         for blk in blocks:
-            h = edgeconv_node_major(blk, h, idx32, sel, dtype)
+            h = edgeconv_node_major(blk, h, ctx, dtype)
         t = ops.linear_f32(h, q[0].w, q[0].b, True, qslope)
         t = ops.linear_f32(t, q[1].w, q[1].b, True, qslope)
         logits = ops.linear_f32(t, q[2].w, q[2].b)
         return logits, h
-    # ---- bf16 fused chains ----
+    # ---- bf16 fused kernels ----
     E = patches.shape[-1]
     if not (E == 64 and _chain_ok(Cg) and pg0.nout == 256 and pg1.nout == 256 and q[0].kin == 256):
         raise RuntimeError("bf16 refine stage supports the shipped dims (num_filters=256, query_dims=(256,256,64)); "
@@ -386,20 +432,41 @@ def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, obj_ids, dt
         ops.chain_fwd(**common, prologue=ops.PRO_LOAD, src=feat, layers=q_layers, out=logits, out_mode=ops.OUT_F32,
                       n_valid=q[2].nout)
         return logits, feat
+    # K3 + pre-graph MLP + first [P|Q] GEMM in one launch
     z = torch.empty((B, N, 2 * preps[0].Co), dtype=torch.bfloat16, device=dev)
     ops.chain_fwd(**common, **taps_args,
                   layers=pg_layers + [ops.chain_layer(preps[0].packed, preps[0].b, preps[0].C, 2 * preps[0].Co, False, 0.0)],
                   out=z, out_mode=ops.OUT_BF16)
+    # EdgeConv j aggregation fused with EdgeConv j+1's [P|Q] GEMM
     for j in range(1, len(blocks)):
         z2 = torch.empty_like(z)
-        ops.chain_fwd(**common, prologue=ops.PRO_AGG, z=z, idx32=idx32, graph_sel=sel, agg_slope=preps[j - 1].slope,
-                      layers=[ops.chain_layer(preps[j].packed, preps[j].b, preps[j].C, 2 * preps[j].Co, False, 0.0)],
-                      out=z2, out_mode=ops.OUT_BF16)
+        _agg_gemm(z, ctx, preps[j - 1].slope,
+                  ops.chain_layer(preps[j].packed, preps[j].b, preps[j].C, 2 * preps[j].Co, False, 0.0), z2, ops.OUT_BF16)
         z = z2
+    # last aggregation (stored: it is the next stage's graph feature) fused with the first query layer, then the rest
     feat = torch.empty((B, N, preps[-1].Co), dtype=torch.bfloat16, device=dev)
-    ops.chain_fwd(**common, prologue=ops.PRO_AGG, z=z, idx32=idx32, graph_sel=sel, agg_slope=preps[-1].slope, a_out=feat,
-                  layers=q_layers, out=logits, out_mode=ops.OUT_F32, n_valid=q[2].nout)
+    hq = torch.empty((B, N, q[0].nout), dtype=torch.bfloat16, device=dev)
+    _agg_gemm(z, ctx, preps[-1].slope, q_layers[0], hq, ops.OUT_BF16, a_out=feat)
+    ops.chain_fwd(**common, prologue=ops.PRO_LOAD, src=hq, layers=q_layers[1:], out=logits, out_mode=ops.OUT_F32,
+                  n_valid=q[2].nout)
     return logits, feat
+
+
+def _stage_ctx(net, ref, obj_ids, B, dev, base_ctx):
+    """GraphCtx of a refine stage; all graphs of one net must share the keypoint renumbering."""
+    blocks = list(ref.pre_query_block)
+    if not blocks:
+        return base_ctx
+    ctx = graph_ctx(blocks[0]._knn, obj_ids, B, dev)
+    if base_ctx is not None and ctx.plan is not base_ctx.plan:
+        key = (id(ctx.plan), id(base_ctx.plan))
+        ok = net.__dict__.setdefault("_cp_perm_ok", {})
+        if key not in ok:
+            ok.clear()
+            ok[key] = bool(torch.equal(ctx.plan.perm, base_ctx.plan.perm))
+        if not ok[key]:
+            raise RuntimeError("the kNN graphs of one net must be built from the same keypoints (their plan orders differ)")
+    return ctx
 
 
 # --------------------------------------------------------------------------------------------------
@@ -413,21 +480,31 @@ def pose_head_forward(net, img_feats, obj_ids=None, stage=None, dtype=None, bbox
     nact = net.num_refine_steps if stage is None else stage
     feat_last = img_feats[-1]
     B, dev, N = feat_last.shape[0], feat_last.device, net.npoint
-    logits0, gfeat = init_head_node_major(net.init_net, feat_last, obj_ids, dtype)
+    logits0, gfeat, ctx0 = init_head_node_major(net.init_net, feat_last, obj_ids, dtype)
+    if ctx0 is None and nact > 0:      # init net without graph modules: take the renumbering of the first refine graph
+        ctx0 = _stage_ctx(net, net.refine_net[0], obj_ids, B, dev, None)
+        if ctx0 is not None:
+            logits0, gfeat = ctx0.to_plan(logits0), ctx0.to_plan(gfeat)
+    perm = None if ctx0 is None or ctx0.plan.identity else ctx0.plan.perm
+    sel = None if ctx0 is None else ctx0.sel
     L0 = (net.init_net.num_out_bits - 1) // 2
     Ltot = L0 + nact
     roi_bit = torch.empty((B, 1, N), dtype=torch.float32, device=dev)
     x_bits = torch.empty((B, Ltot, N), dtype=torch.float32, device=dev)
     y_bits = torch.empty((B, Ltot, N), dtype=torch.float32, device=dev)
-    roi_mask = torch.empty((B, N), dtype=torch.float32, device=dev)
+    roi_mask = torch.empty((B, N), dtype=torch.float32, device=dev)   # plan order, like the ids below
     x_id = torch.empty((B, N), dtype=torch.int64, device=dev)
     y_id = torch.empty((B, N), dtype=torch.int64, device=dev)
-    ops.decode_init(logits0, L0, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id)
+    ops.decode_init(logits0, L0, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id, perm, sel)
     img_feat = feat_last
     for i in range(nact):
         img_feat = image_block(net.up_net[i], img_feat, dtype, skip=img_feats[-i - 1] if i > 0 else None)
-        logits, gfeat = refine_node_major(net.refine_net[i], img_feat, gfeat, roi_mask, x_id, y_id, obj_ids, dtype)
-        ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id)
+        ctx = _stage_ctx(net, net.refine_net[i], obj_ids, B, dev, ctx0)
+        logits, gfeat = refine_node_major(net.refine_net[i], img_feat, gfeat, roi_mask, x_id, y_id, ctx, dtype)
+        ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id, perm, sel)
+    if perm is not None:
+        x_id = ops.permute_rows(x_id.view(B, N, 1), perm, sel, True).view(B, N)
+        y_id = ops.permute_rows(y_id.view(B, N, 1), perm, sel, True).view(B, N)
     seg = image_block(net.seg_block, img_feat, dtype).float().contiguous()
     corr = None
     if bbox is not None:

@@ -54,11 +54,16 @@ class InitNet_GNN(nn.Module):
     def _forward_impl(self, img, obj_ids, return_img_feats, return_graph_feats):
         dtype = head.get_compute_dtype()
         img_feats = self.img_backbone(img)
-        logits, gfeat = head.init_head_node_major(self, img_feats[-1], obj_ids, dtype)
-        out = logits[:, :, :self.num_out_bits].permute(0, 2, 1)  # (B, #bits, N)
+        logits, gfeat, ctx = head.init_head_node_major(self, img_feats[-1], obj_ids, dtype)
+        logits = logits[:, :, :self.num_out_bits].contiguous()
+        if ctx is not None:   # plan order -> the reference's keypoint order
+            logits = ctx.to_keypoints(logits)
+        out = logits.permute(0, 2, 1)  # (B, #bits, N)
         if return_img_feats:
             return out, img_feats
         elif return_graph_feats:
+            if ctx is not None:
+                gfeat = ctx.to_keypoints(gfeat)
             return out, img_feats, ops.convert(gfeat, img_feats[-1].dtype).permute(0, 2, 1)
         return out
 

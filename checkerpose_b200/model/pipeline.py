@@ -84,11 +84,14 @@ class StaticGraph_module(nn.Module):
     def knn_idx(self, value):
         self._knn = value
 
-    def forward(self, x, batch_indices=None):
+    def _forward_impl(self, x, obj_ids):
         dtype = head.get_compute_dtype()
-        idx32, sel = head.graph_select(self._knn, None, x.shape[0], x.device)
-        y = head.edgeconv_node_major(self, ops.to_node_major(x, dtype), idx32, sel, dtype)
-        return _to_io(y, x.dtype)
+        ctx = head.graph_ctx(self._knn, obj_ids, x.shape[0], x.device)
+        y = head.edgeconv_node_major(self, ctx.to_plan(ops.to_node_major(x, dtype)), ctx, dtype)
+        return _to_io(ctx.to_keypoints(y), x.dtype)
+
+    def forward(self, x, batch_indices=None):
+        return self._forward_impl(x, None)
 
 
 def get_MLP_leakyReLU_layers(dims, doLastAct, negative_slope=0.1):
@@ -219,12 +222,20 @@ class Refine_moduleGNN(nn.Module):
 
     def _forward_impl(self, img_feat, graph_feat, roi_mask_bit, prev_x_id, prev_y_id, obj_ids):
         dtype = head.get_compute_dtype()
-        B = img_feat.shape[0]
-        mask = roi_mask_bit.detach().reshape(B, -1).contiguous().float()
-        logits, feat = head.refine_node_major(self, img_feat, ops.to_node_major(graph_feat, dtype), mask,
-                                              prev_x_id, prev_y_id, obj_ids, dtype)
-        output_bits = logits[:, :, :2].permute(0, 2, 1)
-        return output_bits, _to_io(feat, graph_feat.dtype)
+        B, N = img_feat.shape[0], self.npoint
+        blocks = list(self.pre_query_block)
+        ctx = head.graph_ctx(blocks[0]._knn, obj_ids, B, img_feat.device) if blocks else None
+        mask = roi_mask_bit.detach().reshape(B, N, 1).contiguous().float()
+        gfeat = ops.to_node_major(graph_feat, dtype)
+        x_id, y_id = prev_x_id.reshape(B, N, 1).contiguous(), prev_y_id.reshape(B, N, 1).contiguous()
+        if ctx is not None:   # the kernels work in the graph plan's node order; the API is in keypoint order
+            mask, gfeat, x_id, y_id = ctx.to_plan(mask), ctx.to_plan(gfeat), ctx.to_plan(x_id), ctx.to_plan(y_id)
+        logits, feat = head.refine_node_major(self, img_feat, gfeat, mask.view(B, N), x_id.view(B, N), y_id.view(B, N),
+                                              ctx, dtype)
+        logits = logits[:, :, :2].contiguous()
+        if ctx is not None:
+            logits, feat = ctx.to_keypoints(logits), ctx.to_keypoints(feat)
+        return logits.permute(0, 2, 1), _to_io(feat, graph_feat.dtype)
 
     def forward(self, img_feat, graph_feat, p3d_normed, roi_mask_bit, prev_x_id, prev_y_id):
         return self._forward_impl(img_feat, graph_feat, roi_mask_bit, prev_x_id, prev_y_id, None)

@@ -14,10 +14,7 @@ from . import pipeline as _single
 
 class StaticGraph_module(_single.StaticGraph_module):
     def forward(self, x, batch_indices, obj_ids):
-        dtype = head.get_compute_dtype()
-        idx32, sel = head.graph_select(self._knn, obj_ids, x.shape[0], x.device)
-        y = head.edgeconv_node_major(self, ops.to_node_major(x, dtype), idx32, sel, dtype)
-        return _to_io(y, x.dtype)
+        return self._forward_impl(x, obj_ids)
 
 
 class Refine_moduleGNN(_single.Refine_moduleGNN):

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ChainLayer, ChainParams, check, lib
+from ._lib import ChainLayer, ChainParams, EdgeConvParams, GraphPlanStruct, check, lib
 
 CP_F32, CP_BF16 = 0, 1
 PRO_LOAD, PRO_AGG, PRO_TAPS = 0, 1, 2
@@ -284,21 +284,101 @@ def chain_fwd(*, prologue, B, N, layers, out, out_mode, n_valid=0,
     return out
 
 
+# --------------------------------------------------------------------- staged EdgeConv (graph plan)
+PLAN_UMAX = 320
+PLAN_MAX_K = 40
+
+
+class GraphPlan:
+    """Device-resident result of cp_graph_plan_build for a (G,N,K) kNN table (see the header).  ``perm`` maps plan
+    position -> keypoint id; ``idx_p`` is the neighbour table in plan numbering; ``staged`` tells whether every tile's
+    distinct-neighbour list fits the staged kernel's shared-memory buffer."""
+
+    def __init__(self, idx32: torch.Tensor, xyz):
+        """idx32 (G,N,K) int32 tensor in keypoint numbering (the plan lives on its device); xyz (G,3,N) or None."""
+        G, N, K = idx32.shape
+        dev = idx32.device
+        T = (N + 127) // 128
+        KP = (K + 7) // 8 * 8
+        idx_h = idx32.cpu().contiguous()
+        xyz_h = None if xyz is None else xyz.detach().to("cpu", torch.float32).contiguous()
+        if xyz_h is not None and tuple(xyz_h.shape) != (G, 3, N):
+            raise RuntimeError(f"GraphPlan: keypoints {tuple(xyz_h.shape)} do not match the graph table {(G, N, K)}")
+        perm = torch.empty((G, N), dtype=torch.int32)
+        idx_p = torch.empty((G, N, K), dtype=torch.int32)
+        ucount = torch.empty((G, T), dtype=torch.int32)
+        ulist = torch.empty((G, T, PLAN_UMAX), dtype=torch.int32)
+        lidx = torch.empty((G, N, KP), dtype=torch.int16)
+        worst = lib.cp_graph_plan_build(_p(xyz_h), _p(idx_h), G, N, K, PLAN_UMAX, _p(perm), _p(idx_p), _p(ucount), _p(ulist),
+                                        _p(lidx))
+        check(min(worst, 0), "cp_graph_plan_build")
+        self.G, self.N, self.K, self.KP, self.T = G, N, K, KP, T
+        self.max_unique = int(worst)
+        self.staged = worst <= PLAN_UMAX and K <= PLAN_MAX_K
+        self.identity = bool((perm == torch.arange(N, dtype=torch.int32)).all())
+        self.perm = perm.to(dev)
+        self.idx_p = idx_p.to(dev)
+        self.ucount, self.ulist, self.lidx = ucount.to(dev), ulist.to(dev), lidx.to(dev)
+        self.struct = GraphPlanStruct(G, N, K, KP, T, PLAN_UMAX, self.ucount.data_ptr(), self.ulist.data_ptr(),
+                                      self.lidx.data_ptr())
+
+
+def edgeconv_fwd(*, z, plan: GraphPlan, graph_sel, agg_slope, layer, out, out_mode, n_valid=0, a_out=None):
+    """One launch of the staged EdgeConv kernel (cp_edgeconv_fwd).  z (B,N,2Co) bf16 in plan order."""
+    _need_cuda(z, out, a_out, graph_sel)
+    if not plan.staged:
+        raise RuntimeError("edgeconv_fwd: this graph does not fit the staged kernel (see GraphPlan.staged)")
+    assert z.dtype == torch.bfloat16 and z.is_contiguous() and z.shape[1] == plan.N
+    p = EdgeConvParams()
+    p.B, p.N = z.shape[0], z.shape[1]
+    p.z, p.ld_z, p.Co = _p(z), z.shape[-1], z.shape[-1] // 2
+    p.plan, p.graph_sel, p.agg_slope = plan.struct, _p(graph_sel), float(agg_slope)
+    if a_out is not None:
+        assert a_out.dtype == torch.bfloat16 and a_out.is_contiguous()
+        p.a_out, p.ld_a_out = _p(a_out), a_out.shape[-1]
+    p.layer = layer
+    p.out_mode, p.out, p.ld_out, p.n_valid = out_mode, _p(out), out.shape[-1], int(n_valid)
+    if chain_event_log is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.cp_edgeconv_fwd(C.byref(p), _stream()), "cp_edgeconv_fwd")
+        e1.record()
+        chain_event_log.append((("EC", p.Co, (layer.nout,), out_mode, p.B, p.N), e0, e1))
+    else:
+        check(lib.cp_edgeconv_fwd(C.byref(p), _stream()), "cp_edgeconv_fwd")
+    _count()
+    return out
+
+
 # ------------------------------------------------------------------------------------- K4 decode
-def decode_init(logits, L, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id):
-    _need_cuda(logits, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id)
+def decode_init(logits, L, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id, perm=None, graph_sel=None):
+    """perm (G,N) int32: plan position -> keypoint id of the logit rows (None = rows already in keypoint order)."""
+    _need_cuda(logits, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id, perm, graph_sel)
     B, N = x_id.shape
     check(lib.cp_decode_init(_p(logits), logits.shape[-1], L, Ltot, _p(roi_bit), _p(x_bits), _p(y_bits), _p(roi_mask),
-                             _p(x_id), _p(y_id), B, N, _stream()), "cp_decode_init")
+                             _p(x_id), _p(y_id), B, N, _p(perm), _p(graph_sel), _stream()), "cp_decode_init")
     _count()
 
 
-def decode_refine(logits, plane, Ltot, x_bits, y_bits, x_id, y_id):
-    _need_cuda(logits, x_bits, y_bits, x_id, y_id)
+def decode_refine(logits, plane, Ltot, x_bits, y_bits, x_id, y_id, perm=None, graph_sel=None):
+    _need_cuda(logits, x_bits, y_bits, x_id, y_id, perm, graph_sel)
     B, N = x_id.shape
     check(lib.cp_decode_refine(_p(logits), logits.shape[-1], plane, Ltot, _p(x_bits), _p(y_bits), _p(x_id), _p(y_id), B, N,
-                               _stream()), "cp_decode_refine")
+                               _p(perm), _p(graph_sel), _stream()), "cp_decode_refine")
     _count()
+
+
+def permute_rows(x, perm, graph_sel, to_keypoint_order):
+    """x (B,N,...) contiguous -> same shape; rows moved between plan order and keypoint order (cp_permute_rows)."""
+    _need_cuda(x, perm, graph_sel)
+    x = x.contiguous()
+    B, N = x.shape[0], x.shape[1]
+    row_bytes = (x.numel() // (B * N)) * x.element_size()
+    out = torch.empty_like(x)
+    check(lib.cp_permute_rows(_p(x), _p(out), row_bytes, B, N, _p(perm), _p(graph_sel), int(bool(to_keypoint_order)),
+                              _stream()), "cp_permute_rows")
+    _count()
+    return out
 
 
 CORR_DTYPE_BYTES = 12

@@ -130,6 +130,47 @@ typedef struct {
 
 int cp_chain_fwd(const cp_chain_params* p, cp_stream_t s);
 
+/* ---- K2, staged form: graph plan + warp-specialised EdgeConv kernel ----------------------------------
+ * cp_graph_plan_build (HOST pointers, host code; run once per graph next to the knn() call of
+ * pipeline.py:248 / init.py:98): renumbers the keypoints of each graph by recursive coordinate bisection
+ * so that a tile of 128 consecutive nodes is a compact patch, and lists per tile the distinct neighbour
+ * rows the kernel stages in shared memory.
+ *   in : xyz (G,3,N) f32 or NULL (keep numbering), idx (G,N,K) int32, umax = capacity of a tile's list
+ *   out: perm (G,N) int32      perm[g][n'] = original keypoint stored at plan position n'
+ *        idx_p (G,N,K) int32   neighbour lists in plan numbering
+ *        ucount (G,T) int32, ulist (G,T,umax) int32   distinct neighbour positions per tile, T = ceil(N/128)
+ *        lidx (G,N,KP) uint16  position of each neighbour in its tile's list, KP = K rounded up to 8
+ * Returns the largest per-tile count (the staged kernel needs it <= umax) or a negative CP_E_* code. */
+int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, int N, int K, int umax, int32_t* perm,
+                        int32_t* idx_p, int32_t* ucount, int32_t* ulist, uint16_t* lidx);
+#define CP_PLAN_UMAX 320 /* rows of 128 B per staging buffer of cp_edgeconv_fwd */
+
+typedef struct { /* DEVICE pointers to the arrays cp_graph_plan_build produced */
+  int G, N, K, KP, T, umax;
+  const int32_t* ucount;
+  const int32_t* ulist;
+  const uint16_t* lidx;
+} cp_graph_plan;
+
+/* StaticGraph_module (pipeline.py:45-59) in the factored form, fused with the GEMM that consumes it:
+ *   A[i,:]  = lrelu(max_k z[b, nbr(i,k), :Co] + z[b, i, Co:2Co])       (never leaves the SM)
+ *   out     = act(A . W^T + bias)                                       (tcgen05, fp32 accumulate in TMEM)
+ * One persistent CTA per SM; per tile of 128 nodes a producer warp stages the tile's distinct neighbour
+ * rows (64-channel slices of 128 B) in shared memory with bulk-async copies, eight warps take the max
+ * from shared memory in registers and write the bf16 A operand, one thread issues the MMAs against
+ * weights streamed by another producer, and four warps drain TMEM -- all overlapped through mbarriers.
+ * All node-major tensors are in PLAN order.  Co in {64,128,256}; layer.kin == Co; layer.nout <= 512;
+ * K <= 40; every tile's distinct-neighbour count <= CP_PLAN_UMAX. */
+typedef struct {
+  int B, N;
+  const void* z; int ld_z; int Co;
+  cp_graph_plan plan; const int32_t* graph_sel; float agg_slope;
+  void* a_out; int ld_a_out;          /* optional bf16 copy of A (the EdgeConv output feature) */
+  cp_chain_layer layer;
+  int out_mode; void* out; int ld_out; int n_valid;
+} cp_edgeconv_params;
+int cp_edgeconv_fwd(const cp_edgeconv_params* p, cp_stream_t s);
+
 /* ---- K3: Index2Feat 4-tap integer gather (pipeline.py:156-163) + roi-mask multiply (:280) ------
  * patches (B, Hp, Wp, E) NHWC in `dtype`; taps (2y,2x),(2y+k,2x),(2y,2x+k),(2y+k,2x+k), channel order
  * [tap1 | tap2 | tap3 | tap4]; out (B, N, 4E) node-major in `dtype`; mask (B,N) f32 or NULL. */
@@ -147,13 +188,22 @@ int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_
 /* ---- K4: sign-bit decode ------------------------------------------------------------------------
  * Init stage (pipeline.py:363-369): logits (B*N, ld) f32 rows = [roi, x_0..x_{L-1}, y_0..y_{L-1}].
  * Writes roi_bit (B,1,N), planes 0..L-1 of x_bits / y_bits (B, Ltot, N), roi_mask (B,N) f32 {0,1} and
- * ids (B,N) int64 = sum_i bit_i 2^(L-1-i).  bit = logit > 0  (== sigmoid > 0.5 up to |logit| < 2e-7). */
+ * ids (B,N) int64 = sum_i bit_i 2^(L-1-i).  bit = logit > 0  (== sigmoid > 0.5 up to |logit| < 2e-7).
+ * Logit rows, roi_mask and ids are in PLAN order (row n of RoI b is keypoint perm[g(b)][n]; perm (G,N) int32 from
+ * cp_graph_plan_build, graph_sel (B) int32 or NULL => graph 0; perm NULL => identity); roi_bit / x_bits / y_bits
+ * are written in the reference's keypoint order. */
 int cp_decode_init(const float* logits, int ld, int L, int Ltot, float* roi_bit, float* x_bits, float* y_bits,
-                   float* roi_mask, int64_t* x_id, int64_t* y_id, int B, int N, cp_stream_t s);
+                   float* roi_mask, int64_t* x_id, int64_t* y_id, int B, int N, const int32_t* perm,
+                   const int32_t* graph_sel, cp_stream_t s);
 /* Refine stage (pipeline.py:375-381): logits (B*N, ld) rows = [x_new, y_new]; writes plane `plane` of
  * x_bits / y_bits and updates id = 2*id + bit in place. */
 int cp_decode_refine(const float* logits, int ld, int plane, int Ltot, float* x_bits, float* y_bits,
-                     int64_t* x_id, int64_t* y_id, int B, int N, cp_stream_t s);
+                     int64_t* x_id, int64_t* y_id, int B, int N, const int32_t* perm, const int32_t* graph_sel,
+                     cp_stream_t s);
+/* Plan order <-> keypoint order for node-major rows of row_bytes bytes (multiple of 4), out of place:
+ * to_keypoint_order != 0: dst[b, perm[g(b)][n], :] = src[b, n, :];  == 0: dst[b, n, :] = src[b, perm[g(b)][n], :]. */
+int cp_permute_rows(const void* src, void* dst, int row_bytes, int B, int N, const int32_t* perm,
+                    const int32_t* graph_sel, int to_keypoint_order, cp_stream_t s);
 /* Correspondence records, first half of from_id_to_pose (test_network_with_test_data.py:50-66) for the
  * three calls of test.py:335-368, with roi_xy_ori of bop_dataset_pytorch.py:223-235,266-269:
  *   u = bbox.x + x_id * bbox.w / S,  v = bbox.y + y_id * bbox.h / S

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) bulk_kernel(const uint8_t* __restrict__ b
   __syncthreads();
   const int pieces = bufbytes / piece;
   // each CTA walks its own window of the buffer (L2-resident overall)
-  const size_t window = nbytes / gridDim.x;
+  const size_t window = (nbytes / gridDim.x) & ~(size_t)1023;
   const uint8_t* base = buf + (size_t)blockIdx.x * window;
   if (warp == 0) {
     for (int r = 0; r < rounds; ++r) {

@@ -176,3 +176,46 @@ def test_bench_reference_arm_contract():
     assert bench.METRIC.startswith("RoIs/sec") and bench.NPOINT == 4096
     hbm, src = bench.load_peaks()
     assert hbm > 1000 and ("measured" in src or "fallback" in src)
+
+
+# ------------------------------------------------------------------------------------------------ graph plan (host code)
+@pytest.mark.parametrize("ds,objs,N,K", [("lmo", (1,), 4096, 20), ("ycbv", (21,), 512, 20), ("lm", (2, 9), 300, 8), ("lmo", (5,), 1024, 40)])
+def test_graph_plan_invariants(ds, objs, N, K):
+    """cp_graph_plan_build: the renumbering is a permutation, the plan-order neighbour table and the per-tile
+    staging lists reproduce the reference graph exactly, and FPS clouds fit the staged kernel's buffer."""
+    from checkerpose_b200 import ops
+    from checkerpose_b200 import synthetic as syn
+    from oracle import checkerpose_oracle as orc
+    p3d = torch.cat([syn.p3d_normed_tensor(syn.load_fps_xyz(ds, o, N)) for o in objs], dim=0)
+    idx = orc.knn(p3d, K)                                   # (G,N,K) int64, keypoint numbering
+    plan = ops.GraphPlan(idx.to(torch.int32), p3d)
+    G = len(objs)
+    # shipped graph_k = 20 fits the staged kernel's buffer; the K = 40 sweep point falls back to direct gathers
+    assert plan.staged == (plan.max_unique <= ops.PLAN_UMAX) and (plan.staged or K > 20), plan.max_unique
+    perm = plan.perm.long()
+    for g in range(G):
+        assert torch.equal(torch.sort(perm[g])[0], torch.arange(N))
+        # same edges: keypoint ids of the plan-order neighbours == the reference's neighbours of that keypoint
+        assert torch.equal(perm[g][plan.idx_p[g].long()], idx[g][perm[g]])
+        lidx = plan.lidx[g].long() & 0xFFFF
+        for t in range(plan.T):
+            n0, n1 = t * 128, min(N, t * 128 + 128)
+            U = int(plan.ucount[g, t])
+            ul = plan.ulist[g, t].long()
+            assert U == len(torch.unique(plan.idx_p[g, n0:n1]))
+            if U > ops.PLAN_UMAX:
+                continue   # list truncated: the caller must not use the staged kernel (plan.staged is False)
+            assert torch.equal(ul[:U], torch.unique(plan.idx_p[g, n0:n1].long()))
+            assert torch.equal(ul[lidx[n0:n1, :K]], plan.idx_p[g, n0:n1].long())
+            if plan.KP > K:   # padding repeats a real neighbour
+                assert torch.equal(lidx[n0:n1, K:], lidx[n0:n1, :1].expand(-1, plan.KP - K))
+    # locality is the point of the renumbering: far fewer distinct rows per tile than K * 128
+    assert plan.max_unique < 0.2 * 128 * K or N <= 512
+
+
+def test_graph_plan_without_coordinates_keeps_order():
+    from checkerpose_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, 2000, (1, 2000, 12), generator=g, dtype=torch.int32)
+    plan = ops.GraphPlan(idx, None)
+    assert plan.identity and torch.equal(plan.idx_p, idx) and not plan.staged   # random graph: too many distinct rows

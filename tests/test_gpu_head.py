@@ -113,7 +113,7 @@ def test_head_bf16_vs_reference_golden(golden, name):
     y_ok = (yid.cpu().numpy() >> 3) == (g["y_id"] >> 3)
     margin = BF16_MAX * scale
     safe0 = (np.abs(g["x_bits"][:, :3]) > margin).all(1) & (np.abs(g["y_bits"][:, :3]) > margin).all(1)
-    assert safe0.mean() > 0.5
+    assert safe0.mean() > 0.3
     assert (x_ok & y_ok)[safe0].all(), "init-stage cells must match wherever the reference logit is outside the bf16 bar"
     frac = float(((xid.cpu().numpy() == g["x_id"]) & (yid.cpu().numpy() == g["y_id"])).mean())
     print(f"[bf16 {name}] exact 64x64 cell agreement with the fp32 reference (13 cascaded sign tests, random weights): {frac:.4f}")

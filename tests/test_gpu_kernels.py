@@ -346,3 +346,75 @@ def test_upsample2x_cat(cp, dtype, Ca, Cb, H):
     assert out.shape == ref.shape and out.dtype == dtype
     tol = 1e-6 if dtype == torch.float32 else 8e-3   # bf16: one rounding of the output
     assert torch.allclose(out.float().cpu(), ref, rtol=tol, atol=tol)
+
+
+# ------------------------------------------------------------------------------------------------ staged EdgeConv (K2)
+def _fixture_plan(cp, ds, objs, N, K):
+    from oracle import checkerpose_oracle as orc
+    p3d = torch.cat([syn.p3d_normed_tensor(syn.load_fps_xyz(ds, o, N)) for o in objs], dim=0)
+    idx = orc.knn(p3d, K)
+    plan = cp.ops.GraphPlan(idx.to(torch.int32).cuda(), p3d)
+    assert plan.staged
+    return plan
+
+
+@pytest.mark.parametrize("ds,objs,N,K,Co,Nout,B,out_f32", [
+    ("lmo", (1,), 512, 20, 256, 512, 3, False),      # refine-layer shape
+    ("ycbv", (21,), 300, 20, 64, 128, 2, False),     # init-layer shape, ragged last tile
+    ("lm", (2, 9), 256, 8, 128, 256, 4, False),      # per-RoI graphs, K not a multiple of the index vector
+    ("lmo", (5,), 1024, 20, 64, 7, 2, True),         # aggregation -> Linear(64->7) logits in fp32
+    ("lmo", (8,), 4096, 20, 256, 512, 5, False),     # full-size cloud, more tiles than one wave needs
+])
+def test_edgeconv_staged(cp, ds, objs, N, K, Co, Nout, B, out_f32):
+    """cp_edgeconv_fwd vs the same maths in float64 on bf16-representable inputs: the aggregated tile (a_out) must be
+    bit-exact, the GEMM output within fp32-accumulation / bf16-output rounding."""
+    ops = cp.ops
+    plan = _fixture_plan(cp, ds, objs, N, K)
+    G = len(objs)
+    g = torch.Generator().manual_seed(N + K + Co)
+    z = _bf16_round(torch.randn(B, N, 2 * Co, generator=g))
+    sel = torch.randint(0, G, (B,), generator=g).int() if G > 1 else None
+    w = _bf16_round(torch.randn(Nout, Co, generator=g) / Co ** 0.5)
+    bias = torch.randn(Nout, generator=g)
+    idx_p = plan.idx_p.cpu().long()
+    nb = idx_p[sel.long()] if G > 1 else idx_p.expand(B, -1, -1)
+    gat = z[:, :, :Co][torch.arange(B)[:, None, None], nb]                                   # (B,N,K,Co)
+    a_bf = _bf16_round(torch.nn.functional.leaky_relu(gat.max(dim=2)[0] + z[:, :, Co:], 0.2))
+    ref = torch.nn.functional.leaky_relu(a_bf.double() @ w.double().t() + bias.double(), 0.01)
+    a_out = torch.empty((B, N, Co), dtype=torch.bfloat16, device="cuda")
+    layer = ops.chain_layer(ops.pack_weight(w.cuda()), bias.cuda(), Co, Nout, True, 0.01)
+    if out_f32:
+        out = torch.full((B, N, 16), float("nan"), device="cuda")
+        ops.edgeconv_fwd(z=z.cuda().to(torch.bfloat16), plan=plan, graph_sel=None if sel is None else sel.cuda(), agg_slope=0.2,
+                         layer=layer, out=out, out_mode=ops.OUT_F32, n_valid=Nout, a_out=a_out)
+        got = out[:, :, :Nout].cpu().double()
+        tol = 1e-5
+    else:
+        out = torch.empty((B, N, Nout), dtype=torch.bfloat16, device="cuda")
+        ops.edgeconv_fwd(z=z.cuda().to(torch.bfloat16), plan=plan, graph_sel=None if sel is None else sel.cuda(), agg_slope=0.2,
+                         layer=layer, out=out, out_mode=ops.OUT_BF16, a_out=a_out)
+        got = out.cpu().double()
+        tol = 1e-2
+    torch.cuda.synchronize()
+    assert torch.equal(a_out.cpu().float(), a_bf), "aggregated tile must be bit-exact in bf16"
+    assert torch.allclose(got, ref, rtol=tol, atol=tol), float((got - ref).abs().max())
+    # same result as the unstaged kernel (direct global gathers) on the plan-order neighbour table
+    out2 = torch.empty((B, N, Nout if not out_f32 else 16), dtype=out.dtype, device="cuda")
+    a2 = torch.empty_like(a_out)
+    ops.chain_fwd(prologue=ops.PRO_AGG, B=B, N=N, z=z.cuda().to(torch.bfloat16), idx32=plan.idx_p, graph_sel=None if sel is None else sel.cuda(),
+                  agg_slope=0.2, a_out=a2, layers=[layer], out=out2, out_mode=ops.OUT_F32 if out_f32 else ops.OUT_BF16, n_valid=Nout)
+    assert torch.equal(a2, a_out)
+    assert torch.equal(out2[:, :, :Nout], out[:, :, :Nout])
+
+
+def test_permute_rows_roundtrip(cp):
+    plan = _fixture_plan(cp, "lm", (3, 7), 300, 20)
+    B = 5
+    sel = torch.tensor([1, 0, 0, 1, 1], dtype=torch.int32).cuda()
+    for t in (torch.randn(B, 300, 64).cuda(), torch.randn(B, 300, 7).cuda().to(torch.bfloat16).view(B, 300, 7)[:, :, :6].contiguous(),
+              torch.arange(B * 300).view(B, 300, 1).cuda()):
+        p = cp.ops.permute_rows(t, plan.perm, sel, False)
+        perm = plan.perm[sel.long()].long()                                     # (B,N)
+        want = torch.gather(t, 1, perm[:, :, None].expand(-1, -1, t.shape[2]))
+        assert torch.equal(p, want)
+        assert torch.equal(cp.ops.permute_rows(p, plan.perm, sel, True), t)

@@ -6,12 +6,12 @@
 //
 //   warp 2      stage producer: for every 64-channel slice of a 128-node tile it copies the tile's DISTINCT
 //               neighbour rows (plan.ulist, ~240 rows x 128 B instead of 128 x K gathered rows) from the [P|Q]
-//               table into a shared-memory staging buffer with cp.async.bulk (TMA engine), two buffers deep,
-//               and the tile's local neighbour indices (plan.lidx) once per tile;
+//               table into a shared-memory staging buffer with cp.async (LDGSTS, completion on an mbarrier), two
+//               buffers deep, and the tile's local neighbour indices (plan.lidx) once per tile;
 //   warps 8-15  aggregators: quarter-warps own nodes; each takes max_k over its staged neighbour rows with
 //               128-bit shared-memory loads, adds the node's own Q slice, applies LeakyReLU and writes the
 //               bf16 A operand slice straight into the SWIZZLE_128B layout tcgen05.mma reads;
-//   warp 1      weight producer: streams the packed weight tiles (16 KB) through a 3-stage ring;
+//   warp 1      weight producer: streams the packed weight tiles (16 KB) with cp.async.bulk (TMA engine), 3-stage ring;
 //   warp 0      one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete;
 //   warps 4-7   epilogue: TMEM -> registers -> bias / LeakyReLU -> bf16 (or fp32 logits) -> global.
 //
@@ -27,26 +27,34 @@ using namespace sm100;
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NTHREADS = 512;
-constexpr int AGG_WARP0 = 8, NUM_AGG_WARPS = 8;
+constexpr int SUB_M = CP_PLAN_GROUP;         // nodes per staging round (one distinct-row list per group)
+constexpr int NUM_WARPS = 24;
+constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int EPI_WARP0 = 4;
+constexpr int AGG_WARP0 = 8, NUM_AGG_WARPS = 16;   // 64 quarter-warps: one node each per staging round
 constexpr int A_CHUNK_BYTES = TILE_M * 128;  // 128 rows x 64 bf16
 constexpr int A_CHUNKS = 4;
 constexpr int B_STAGE_BYTES = 128 * 128;
 constexpr int B_STAGES = 3;
 constexpr int UMAX = CP_PLAN_UMAX;
 constexpr int STG_BYTES = UMAX * 128;
-constexpr int KP_MAX = 40;
+constexpr int KP_MAX = 32;
 constexpr int LIDX_BYTES = TILE_M * KP_MAX * 2;
+constexpr int TBUF_BYTES = 32 * 128;         // per epilogue warp: 32 rows x 64 bf16, transposed for coalesced stores
+constexpr int BIAS_BYTES = 512 * 4;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_WTILES = 16;
+static_assert(SUB_M * 2 == TILE_M && NUM_AGG_WARPS * 4 == SUB_M, "one quarter-warp per node of a staging group");
 
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_CHUNKS * A_CHUNK_BYTES;
 constexpr int OFF_STG = OFF_B + B_STAGES * B_STAGE_BYTES;
 constexpr int OFF_LIDX = OFF_STG + 2 * STG_BYTES;
-constexpr int OFF_BAR = OFF_LIDX + 2 * LIDX_BYTES;
+constexpr int OFF_TBUF = OFF_LIDX + 2 * LIDX_BYTES;
+constexpr int OFF_BIAS = OFF_TBUF + 4 * TBUF_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
 constexpr int SMEM_BYTES = 1024 + OFF_BAR + 256;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct WTile {
   const uint8_t* ptr;
@@ -59,7 +67,8 @@ struct EcParams {
   int KC;            // 64-channel slices of the aggregated feature (= GEMM K chunks)
   int NB;            // 128-column blocks of the GEMM output
   int npad;          // nout rounded up to 16
-  int num_tiles;     // B * plan.T
+  int num_tiles;     // B * ceil(N / 128)
+  int tiles_per_roi;
   WTile wt[MAX_WTILES];  // order: slice-major, then column block
 };
 
@@ -118,47 +127,77 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // role bodies
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tile_coords(const EcParams& kp, int tile, int& b, int& t, int& g) {
-  b = tile / kp.p.plan.T;
-  t = tile - b * kp.p.plan.T;
+  b = tile / kp.tiles_per_roi;
+  t = tile - b * kp.tiles_per_roi;
   g = kp.p.graph_sel ? __ldg(kp.p.graph_sel + b) : 0;
 }
 
+// cp.async (LDGSTS): 16 bytes per lane, no register staging.  A warp instruction moves four 128-byte row slices;
+// measured on B200, per-row cp.async.bulk copies cost ~55 clk each on the issuing warp (scripts/ubench/membw.cu:
+// 2.3 B/clk/SM at 128 B pieces) and would make the producer the bottleneck, so the TMA engine is kept for the
+// 16 KB weight tiles and row slices go through LDGSTS.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (does not change the expected count)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Staging rounds of a tile: for each 64-channel slice c, for each half h of the tile (64 nodes).
 __device__ void stage_producer(const EcParams& kp, uint8_t* sm, Bars* bars, int lane) {
   const cp_edgeconv_params& p = kp.p;
   const cp_graph_plan& pl = p.plan;
   const uint32_t row_bytes = (uint32_t)p.ld_z * 2;
+  const int grp = lane >> 3, sub = lane & 7;
+  const uint32_t sm_base = smem_u32(sm);
   uint32_t it = 0;  // staging rounds issued
   int ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     int b, t, g;
     tile_coords(kp, tile, b, t, g);
-    const int U = __ldg(pl.ucount + (size_t)g * pl.T + t);
-    const int32_t* ul = pl.ulist + ((size_t)g * pl.T + t) * pl.umax;
-    const uint8_t* zb = reinterpret_cast<const uint8_t*>(p.z) + (size_t)b * p.N * row_bytes;
-    uint32_t src_off[UMAX / 32];  // byte offset of each of this lane's rows inside the RoI's table
-#pragma unroll
-    for (int q = 0; q < UMAX / 32; ++q) {
-      const int u = q * 32 + lane;
-      src_off[q] = (u < U) ? (uint32_t)__ldg(ul + u) * row_bytes : 0u;
-    }
+    const uint8_t* zb = reinterpret_cast<const uint8_t*>(p.z) + (size_t)b * p.N * row_bytes + sub * 16;
     const int rows_valid = min(TILE_M, p.N - t * TILE_M);
-    const uint32_t lidx_bytes = (uint32_t)rows_valid * pl.KP * 2;
-    for (int c = 0; c < kp.KC; ++c, ++it) {
-      const int buf = it & 1;
-      const uint32_t use = it >> 1;
-      if (use > 0) mbar_wait(&bars->stg_empty[buf], (use - 1) & 1);
-      uint64_t* full = &bars->stg_full[buf];
-      if (lane == 0) {
-        mbar_arrive_expect_tx(full, (uint32_t)U * 128u + (c == 0 ? lidx_bytes : 0u));
-        if (c == 0)
-          bulk_g2s(sm + OFF_LIDX + (ti & 1) * LIDX_BYTES, pl.lidx + ((size_t)g * pl.N + (size_t)t * TILE_M) * pl.KP, lidx_bytes, full);
-      }
-      uint8_t* dst = sm + OFF_STG + buf * STG_BYTES;
-      const uint8_t* src = zb + c * 128;
+    const int nhalf = rows_valid > SUB_M ? 2 : 1;
+    int U[2];
+    uint32_t src_off[2][UMAX / 32];  // lane l holds the table offsets of list entries l, l+32, ... of each half
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const size_t grp_id = (size_t)g * pl.T + (size_t)t * 2 + h;
+      U[h] = (h < nhalf) ? __ldg(pl.ucount + grp_id) : 0;
+      const int32_t* ul = pl.ulist + grp_id * pl.umax;
 #pragma unroll
       for (int q = 0; q < UMAX / 32; ++q) {
         const int u = q * 32 + lane;
-        if (u < U) bulk_g2s(dst + u * 128, src + src_off[q], 128, full);
+        src_off[h][q] = (u < U[h]) ? (uint32_t)__ldg(ul + u) * row_bytes : 0u;
+      }
+    }
+    const int lidx_pieces = (rows_valid * pl.KP * 2) >> 4;
+    for (int c = 0; c < kp.KC; ++c) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = it >> 1;
+        if (use > 0) mbar_wait(&bars->stg_empty[buf], (use - 1) & 1);
+        if (c == 0 && h == 0) {  // the tile's local neighbour offsets ride on the first round's barrier
+          const uint8_t* ls = reinterpret_cast<const uint8_t*>(pl.lidx + ((size_t)g * pl.N + (size_t)t * TILE_M) * pl.KP);
+          const uint32_t ld = sm_base + OFF_LIDX + (ti & 1) * LIDX_BYTES;
+          for (int q = lane; q < lidx_pieces; q += 32) cp_async16(ld + q * 16, ls + q * 16);
+        }
+        const uint32_t dst = sm_base + OFF_STG + buf * STG_BYTES + sub * 16;
+        const uint8_t* src = zb + c * 128;
+#pragma unroll
+        for (int q = 0; q < UMAX / 32; ++q) {  // 32 list entries per register of src_off
+          if (q * 32 < U[h]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {      // four list entries (row slices of 128 B) per warp instruction
+              const uint32_t off = __shfl_sync(0xffffffffu, src_off[h][q], j * 4 + grp);
+              const int u = q * 32 + j * 4 + grp;
+              if (u < U[h]) cp_async16(dst + u * 128, src + off);
+            }
+          }
+        }
+        cp_async_arrive_noinc(&bars->stg_full[buf]);
       }
     }
   }
@@ -208,11 +247,26 @@ __device__ void mma_issuer(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t
   }
 }
 
+// max over four staged rows; written so that ptxas pairs the maxima into 3-input VHMNMX
+__device__ __forceinline__ uint4 max_quad(uint4 m, bool have, uint32_t stg, uint32_t w0, uint32_t w1) {
+  const uint4 v0 = lds128(stg + (w0 & 0xffffu)), v1 = lds128(stg + (w0 >> 16));
+  const uint4 v2 = lds128(stg + (w1 & 0xffffu)), v3 = lds128(stg + (w1 >> 16));
+  uint4 r;
+  if (have) {
+    r = bf8_max(bf8_max(m, v0), v1);
+    r = bf8_max(bf8_max(r, v2), v3);
+  } else {
+    r = bf8_max(bf8_max(v0, v1), v2);
+    r = bf8_max(r, v3);
+  }
+  return r;
+}
+
 __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, int lane) {
   const cp_edgeconv_params& p = kp.p;
   const int KP = p.plan.KP, K = p.plan.K;
   const int lg = lane >> 3, sub = lane & 7;
-  const int gid = aw * 4 + lg;  // quarter-warp id, 0..31: owns rows 4*gid .. 4*gid+3 of the tile
+  const int qw = aw * 4 + lg;  // quarter-warp id, 0..63: owns node qw of each half tile
   const uint32_t sm_base = smem_u32(sm);
   const float slope = p.agg_slope;
   uint32_t it = 0;
@@ -226,82 +280,69 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     const bf16* zq = reinterpret_cast<const bf16*>(p.z) + row0 * p.ld_z + p.Co + sub * 8;  // own Q slices
     bf16* aout = p.a_out ? reinterpret_cast<bf16*>(p.a_out) + row0 * p.ld_a_out + sub * 8 : nullptr;
     const uint32_t lidx_s = sm_base + OFF_LIDX + (ti & 1) * LIDX_BYTES;
-    for (int c = 0; c < kp.KC; ++c, ++it) {
-      const int buf = it & 1;
-      // own Q slices first: their latency hides behind the barrier waits
-      uint4 q[4];
+    for (int c = 0; c < kp.KC; ++c) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = gid * 4 + j;
-        q[j] = (r < rows_valid) ? ldg_nc_v4(zq + (size_t)r * p.ld_z + c * 64) : make_uint4(0, 0, 0, 0);
-      }
-      mbar_wait(&bars->stg_full[buf], (it >> 1) & 1);
-      if (ti > 0) mbar_wait(&bars->a_empty[c], (ti - 1) & 1);
-      const uint32_t stg = sm_base + OFF_STG + buf * STG_BYTES + sub * 16;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = gid * 4 + j;
+      for (int h = 0; h < 2; ++h, ++it) {
+        const int buf = it & 1;
+        const int r = h * SUB_M + qw;
+        const bool valid = r < rows_valid;
+        // own Q slice first: its latency hides behind the barrier waits
+        const uint4 q = valid ? ldg_nc_v4(zq + (size_t)r * p.ld_z + c * 64) : make_uint4(0, 0, 0, 0);
+        mbar_wait(&bars->stg_full[buf], (it >> 1) & 1);
+        if (h == 0 && ti > 0) mbar_wait(&bars->a_empty[c], (ti - 1) & 1);
         uint4 o = make_uint4(0, 0, 0, 0);
-        if (r < rows_valid) {
+        if (valid) {
+          const uint32_t stg = sm_base + OFF_STG + buf * STG_BYTES + sub * 16;
           const uint32_t li = lidx_s + (uint32_t)(r * KP) * 2;
           uint4 m = make_uint4(0, 0, 0, 0);
           for (int k0 = 0; k0 < K; k0 += 8) {
-            const uint4 iv = lds128(li + k0 * 2);  // 8 local indices (broadcast within the quarter-warp)
-            const uint32_t w[4] = {iv.x, iv.y, iv.z, iv.w};
-            uint4 mm;
-            if (K - k0 >= 8) {
-              uint4 v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const uint32_t l = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
-                v[e] = lds128(stg + l * 128);
-              }
-              mm = bf8_max(bf8_max(bf8_max(v[0], v[1]), bf8_max(v[2], v[3])), bf8_max(bf8_max(v[4], v[5]), bf8_max(v[6], v[7])));
-            } else {  // tail of the neighbour list (warp-uniform trip count)
-              mm = lds128(stg + (w[0] & 0xffffu) * 128);
-#pragma unroll
-              for (int e = 1; e < 8; ++e) {
-                if (e < K - k0) {
-                  const uint32_t l = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
-                  mm = bf8_max(mm, lds128(stg + l * 128));
-                }
-              }
+            const uint4 iv = lds128(li + k0 * 2);  // 8 byte offsets into the staging buffer (broadcast load)
+            const int n = K - k0;                   // warp-uniform
+            m = max_quad(m, k0 > 0, stg, iv.x, iv.y);
+            if (n >= 8) {
+              m = max_quad(m, true, stg, iv.z, iv.w);
+            } else if (n > 4) {  // padding entries repeat the node's first neighbour: harmless under max
+              m = max_quad(m, true, stg, iv.z, iv.w);
             }
-            m = (k0 == 0) ? mm : bf8_max(m, mm);
           }
-          const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, qw[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+          const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, qv[4] = {q.x, q.y, q.z, q.w};
           uint32_t ow[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 a = bf2_to_f2(mw[e]), d = bf2_to_f2(qw[e]);
+            const float2 a = bf2_to_f2(mw[e]), d = bf2_to_f2(qv[e]);
             ow[e] = f2_to_bf2(cp::lrelu(a.x + d.x, slope), cp::lrelu(a.y + d.y, slope));
           }
           o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           if (aout) *reinterpret_cast<uint4*>(aout + (size_t)r * p.ld_a_out + c * 64) = o;
         }
         sts128(sm_base + a_offset(c, r, sub), o);
-      }
-      fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core's async proxy
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bars->a_full[c]);
-        mbar_arrive(&bars->stg_empty[buf]);
+        fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars->a_full[c]);
+          mbar_arrive(&bars->stg_empty[buf]);
+        }
       }
     }
   }
 }
 
-__device__ void epilogue_warps(const EcParams& kp, Bars* bars, uint32_t tmem_base, int q, int lane) {
+__device__ void epilogue_warps(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base, int q, int lane) {
   const cp_edgeconv_params& p = kp.p;
   const cp_chain_layer& L = p.layer;
   const int row = q * 32 + lane;
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+  const uint32_t sm_base = smem_u32(sm);
+  const uint32_t tbuf = sm_base + OFF_TBUF + q * TBUF_BYTES;
+  const uint32_t bias_s = sm_base + OFF_BIAS;
+  const bool transposed = (p.out_mode == CP_OUT_BF16) && (kp.npad % 64 == 0);
   int ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
-    const int b = tile / p.plan.T, t = tile - b * p.plan.T;
+    const int b = tile / kp.tiles_per_roi, t = tile - b * kp.tiles_per_roi;
     const int n0 = t * TILE_M;
-    const bool row_ok = row < min(TILE_M, p.N - n0);
-    const size_t grow = (size_t)b * p.N + n0 + row;
+    const int rows_valid = min(TILE_M, p.N - n0);
+    const bool row_ok = row < rows_valid;
+    const size_t grow0 = (size_t)b * p.N + n0;
     mbar_wait(&bars->acc_full, ti & 1);
     tc_fence_after_sync();
     for (int c0 = 0; c0 < kp.npad; c0 += 32) {
@@ -315,29 +356,55 @@ __device__ void epilogue_warps(const EcParams& kp, Bars* bars, uint32_t tmem_bas
         for (int e = 0; e < 16; ++e) { r[e] = h[e]; r[16 + e] = 0; }
       }
       tmem_ld_wait();
-      const int ncols = min(32, kp.npad - c0);
       float v[32];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        float x = __uint_as_float(r[e]);
-        if (L.bias && c0 + e < L.nout) x += __ldg(L.bias + c0 + e);
-        if (L.act) x = cp::lrelu(x, L.slope);
-        v[e] = x;
-      }
-      if (!row_ok) continue;
-      if (p.out_mode == CP_OUT_BF16) {
-        bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ld_out + c0;
+      for (int e4 = 0; e4 < 8; ++e4) {
+        const uint4 bb = lds128(bias_s + (uint32_t)(c0 + e4 * 4) * 4);  // zero-filled when the layer has no bias
+        const float bv[4] = {__uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          if (e * 8 < ncols)
-            *reinterpret_cast<uint4*>(o + e * 8) = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
-                                                              f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
+          float x = __uint_as_float(r[e4 * 4 + e]) + bv[e];
+          if (L.act) x = cp::lrelu(x, L.slope);
+          v[e4 * 4 + e] = x;
         }
-      } else {
-        float* o = reinterpret_cast<float*>(p.out) + grow * p.ld_out;
+      }
+      if (transposed) {
+        // 32 columns = 64 B per row into the warp's 32 x 128 B transposition tile (16-byte chunks XOR-swizzled by row)
+        const int half = (c0 >> 5) & 1;
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (c0 + e < p.n_valid) o[c0 + e] = v[e];
+        for (int e = 0; e < 4; ++e) {
+          const uint4 w = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
+                                     f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
+          sts128(tbuf + lane * 128 + (((half * 4 + e) ^ (lane & 7)) << 4), w);
+        }
+        if (half == 1) {
+          __syncwarp();
+          const int rr = lane >> 3, ch = lane & 7;
+          bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + q * 32) * p.ld_out + (c0 - 32) + ch * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // a quarter-warp stores one full 128-byte line of one row
+            const int lr = i * 4 + rr;
+            const uint4 w = lds128(tbuf + lr * 128 + ((ch ^ (lr & 7)) << 4));
+            if (q * 32 + lr < rows_valid) *reinterpret_cast<uint4*>(o + (size_t)lr * p.ld_out) = w;
+          }
+          __syncwarp();
+        }
+      } else if (row_ok) {
+        const int ncols = min(32, kp.npad - c0);
+        if (p.out_mode == CP_OUT_BF16) {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + row) * p.ld_out + c0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (e * 8 < ncols)
+              *reinterpret_cast<uint4*>(o + e * 8) = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
+                                                                f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + (grow0 + row) * p.ld_out;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e < p.n_valid) o[c0 + e] = v[e];
+        }
       }
     }
     tc_fence_before_sync();
@@ -354,11 +421,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars->stg_full[s], 1);
+      mbar_init(&bars->stg_full[s], 32);  // every lane of the stage producer arrives when its cp.async landed
       mbar_init(&bars->stg_empty[s], NUM_AGG_WARPS);
     }
     for (int c = 0; c < A_CHUNKS; ++c) {
-      mbar_init(&bars->a_full[c], NUM_AGG_WARPS);
+      mbar_init(&bars->a_full[c], NUM_AGG_WARPS * 2);  // both half-tile rounds of a slice
       mbar_init(&bars->a_empty[c], 1);
     }
     for (int s = 0; s < B_STAGES; ++s) {
@@ -370,6 +437,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_slot, TMEM_COLS);
+  for (int i = threadIdx.x; i < BIAS_BYTES / 4; i += NTHREADS)   // bias row (zero-padded) for the epilogue's broadcast loads
+    reinterpret_cast<float*>(sm + OFF_BIAS)[i] = (kp.p.layer.bias && i < kp.p.layer.nout) ? kp.p.layer.bias[i] : 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -384,8 +453,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
   } else if (warp == 2) {
     stage_producer(kp, sm, bars, lane);
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
-    epilogue_warps(kp, bars, tmem_base, warp - EPI_WARP0, lane);
-  } else if (warp >= AGG_WARP0) {
+    epilogue_warps(kp, sm, bars, tmem_base, warp - EPI_WARP0, lane);
+  } else if (warp >= AGG_WARP0 && warp < AGG_WARP0 + NUM_AGG_WARPS) {
     aggregator(kp, sm, bars, warp - AGG_WARP0, lane);
   }
 
@@ -405,7 +474,7 @@ extern "C" int cp_edgeconv_fwd(const cp_edgeconv_params* pp, cp_stream_t s) {
   CP_REQUIRE(p.Co == 64 || p.Co == 128 || p.Co == 256, CP_E_UNSUPPORTED, "cp_edgeconv_fwd: Co=%d not in {64,128,256}", p.Co);
   CP_REQUIRE(p.ld_z >= 2 * p.Co && (p.ld_z % 8) == 0 && (reinterpret_cast<uintptr_t>(p.z) & 15) == 0, CP_E_INVALID,
              "cp_edgeconv_fwd: z must be 16-byte aligned with ld_z %% 8 == 0 and ld_z >= 2*Co (ld_z=%d)", p.ld_z);
-  CP_REQUIRE(pl.ucount && pl.ulist && pl.lidx && pl.N == p.N && pl.T == (p.N + TILE_M - 1) / TILE_M && pl.G >= 1, CP_E_INVALID,
+  CP_REQUIRE(pl.ucount && pl.ulist && pl.lidx && pl.N == p.N && pl.T == (p.N + SUB_M - 1) / SUB_M && pl.G >= 1, CP_E_INVALID,
              "cp_edgeconv_fwd: graph plan does not match N=%d", p.N);
   CP_REQUIRE(pl.K >= 1 && pl.KP == (pl.K + 7) / 8 * 8 && pl.KP <= KP_MAX, CP_E_UNSUPPORTED, "cp_edgeconv_fwd: K=%d outside [1,%d]", pl.K, KP_MAX);
   CP_REQUIRE(pl.umax == UMAX, CP_E_INVALID, "cp_edgeconv_fwd: plan.umax=%d, expected %d", pl.umax, UMAX);
@@ -419,7 +488,8 @@ extern "C" int cp_edgeconv_fwd(const cp_edgeconv_params* pp, cp_stream_t s) {
   kp.npad = (L.nout + 15) & ~15;
   CP_REQUIRE(kp.npad <= TMEM_COLS, CP_E_UNSUPPORTED, "cp_edgeconv_fwd: nout=%d > 512", L.nout);
   kp.NB = (kp.npad + 127) / 128;
-  kp.num_tiles = p.B * pl.T;
+  kp.tiles_per_roi = (p.N + TILE_M - 1) / TILE_M;
+  kp.num_tiles = p.B * kp.tiles_per_roi;
   if (p.out_mode == CP_OUT_BF16)
     CP_REQUIRE((p.ld_out % 8) == 0 && p.ld_out >= kp.npad, CP_E_INVALID, "cp_edgeconv_fwd: bf16 output needs ld_out %% 8 == 0 and >= %d", kp.npad);
   else

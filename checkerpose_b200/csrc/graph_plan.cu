@@ -5,7 +5,7 @@
 // 20 neighbours of 128 consecutive keypoints touch ~2000 distinct rows.  This routine, run once next to that
 // knn() call, renumbers the keypoints by recursive coordinate bisection so that every tile of 128
 // consecutive nodes is a compact surface patch (its neighbour lists then touch ~240 distinct rows), and
-// precomputes per tile the list of distinct neighbour rows ("ulist", what the kernel stages in shared
+// precomputes per group of 64 nodes the list of distinct neighbour rows ("ulist", what the kernel stages in shared
 // memory with bulk-async copies) and, per edge, the position of the neighbour in that list ("lidx").
 // Pure integer/geometry preprocessing on the host; nothing here is on the per-RoI path.
 #include <algorithm>
@@ -16,7 +16,8 @@
 
 namespace {
 
-constexpr int TILE = 128;
+constexpr int TILE = 128;            // nodes per MMA tile: RCB boxes are whole tiles above this size
+constexpr int GROUP = CP_PLAN_GROUP;  // nodes per staging group (one distinct-row list each)
 
 struct Rcb {
   const float* x;  // (3, N) coordinates of one graph
@@ -58,8 +59,8 @@ struct Rcb {
 extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, int N, int K, int umax, int32_t* perm,
                                    int32_t* idx_p, int32_t* ucount, int32_t* ulist, uint16_t* lidx) {
   CP_REQUIRE(idx && perm && idx_p && ucount && ulist && lidx, CP_E_INVALID, "cp_graph_plan_build: null pointer");
-  CP_REQUIRE(G > 0 && N > 0 && K > 0 && umax > 0 && umax <= 65535, CP_E_INVALID, "cp_graph_plan_build: bad sizes G=%d N=%d K=%d umax=%d", G, N, K, umax);
-  const int T = (N + TILE - 1) / TILE;
+  CP_REQUIRE(G > 0 && N > 0 && K > 0 && umax > 0 && umax <= 511, CP_E_INVALID, "cp_graph_plan_build: bad sizes G=%d N=%d K=%d umax=%d", G, N, K, umax);
+  const int T = (N + GROUP - 1) / GROUP;
   const int KP = (K + 7) / 8 * 8;
   int worst = 0;
   std::vector<int> ids(N), inv(N), stamp(N), local(N);
@@ -85,7 +86,7 @@ extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, 
     std::fill(stamp.begin(), stamp.end(), -1);
     for (int t = 0; t < T; ++t) {
       int32_t* ul = ulist + ((size_t)g * T + t) * umax;
-      const int n0 = t * TILE, n1 = std::min(N, n0 + TILE);
+      const int n0 = t * GROUP, n1 = std::min(N, n0 + GROUP);
       // distinct neighbour rows of the tile, ascending (sequential-ish source addresses for the copies)
       std::vector<int> u;
       for (int i = n0; i < n1; ++i)
@@ -107,7 +108,8 @@ extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, 
       for (int q = U; q < umax; ++q) ul[q] = 0;
       for (int i = n0; i < n1; ++i) {
         uint16_t* li = lidx + ((size_t)g * N + i) * KP;
-        for (int k = 0; k < K; ++k) li[k] = (uint16_t)std::min(local[ip[(size_t)i * K + k]], 65535);
+        // byte offset of the staged row slice; lists longer than umax are truncated and the plan is then unusable
+        for (int k = 0; k < K; ++k) li[k] = (uint16_t)(std::min(local[ip[(size_t)i * K + k]], umax - 1) * 128);
         for (int k = K; k < KP; ++k) li[k] = li[0];  // padding repeats a real neighbour: harmless under max
       }
     }

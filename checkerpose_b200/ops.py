@@ -285,8 +285,9 @@ def chain_fwd(*, prologue, B, N, layers, out, out_mode, n_valid=0,
 
 
 # --------------------------------------------------------------------- staged EdgeConv (graph plan)
-PLAN_UMAX = 320
-PLAN_MAX_K = 40
+PLAN_UMAX = 288     # CP_PLAN_UMAX
+PLAN_GROUP = 64     # CP_PLAN_GROUP
+PLAN_MAX_K = 32
 
 
 class GraphPlan:
@@ -298,7 +299,7 @@ class GraphPlan:
         """idx32 (G,N,K) int32 tensor in keypoint numbering (the plan lives on its device); xyz (G,3,N) or None."""
         G, N, K = idx32.shape
         dev = idx32.device
-        T = (N + 127) // 128
+        T = (N + PLAN_GROUP - 1) // PLAN_GROUP
         KP = (K + 7) // 8 * 8
         idx_h = idx32.cpu().contiguous()
         xyz_h = None if xyz is None else xyz.detach().to("cpu", torch.float32).contiguous()

@@ -133,17 +133,19 @@ int cp_chain_fwd(const cp_chain_params* p, cp_stream_t s);
 /* ---- K2, staged form: graph plan + warp-specialised EdgeConv kernel ----------------------------------
  * cp_graph_plan_build (HOST pointers, host code; run once per graph next to the knn() call of
  * pipeline.py:248 / init.py:98): renumbers the keypoints of each graph by recursive coordinate bisection
- * so that a tile of 128 consecutive nodes is a compact patch, and lists per tile the distinct neighbour
- * rows the kernel stages in shared memory.
- *   in : xyz (G,3,N) f32 or NULL (keep numbering), idx (G,N,K) int32, umax = capacity of a tile's list
+ * so that consecutive nodes form compact patches, and lists for every group of CP_PLAN_GROUP (64)
+ * consecutive nodes the distinct neighbour rows the kernel stages in shared memory.
+ *   in : xyz (G,3,N) f32 or NULL (keep numbering), idx (G,N,K) int32, umax = capacity of a group's list
  *   out: perm (G,N) int32      perm[g][n'] = original keypoint stored at plan position n'
  *        idx_p (G,N,K) int32   neighbour lists in plan numbering
- *        ucount (G,T) int32, ulist (G,T,umax) int32   distinct neighbour positions per tile, T = ceil(N/128)
- *        lidx (G,N,KP) uint16  position of each neighbour in its tile's list, KP = K rounded up to 8
- * Returns the largest per-tile count (the staged kernel needs it <= umax) or a negative CP_E_* code. */
+ *        ucount (G,T) int32, ulist (G,T,umax) int32   distinct neighbour positions per group, T = ceil(N/64)
+ *        lidx (G,N,KP) uint16  128 * (position of each neighbour in its group's list) = byte offset of the
+ *                              staged 128-byte row slice; KP = K rounded up to 8, padding repeats entry 0
+ * Returns the largest per-group count (the staged kernel needs it <= umax) or a negative CP_E_* code. */
 int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, int N, int K, int umax, int32_t* perm,
                         int32_t* idx_p, int32_t* ucount, int32_t* ulist, uint16_t* lidx);
-#define CP_PLAN_UMAX 320 /* rows of 128 B per staging buffer of cp_edgeconv_fwd */
+#define CP_PLAN_GROUP 64 /* nodes per staging round of cp_edgeconv_fwd */
+#define CP_PLAN_UMAX 288 /* rows of 128 B per staging buffer of cp_edgeconv_fwd (umax must be <= 511) */
 
 typedef struct { /* DEVICE pointers to the arrays cp_graph_plan_build produced */
   int G, N, K, KP, T, umax;
@@ -155,12 +157,13 @@ typedef struct { /* DEVICE pointers to the arrays cp_graph_plan_build produced *
 /* StaticGraph_module (pipeline.py:45-59) in the factored form, fused with the GEMM that consumes it:
  *   A[i,:]  = lrelu(max_k z[b, nbr(i,k), :Co] + z[b, i, Co:2Co])       (never leaves the SM)
  *   out     = act(A . W^T + bias)                                       (tcgen05, fp32 accumulate in TMEM)
- * One persistent CTA per SM; per tile of 128 nodes a producer warp stages the tile's distinct neighbour
- * rows (64-channel slices of 128 B) in shared memory with bulk-async copies, eight warps take the max
- * from shared memory in registers and write the bf16 A operand, one thread issues the MMAs against
- * weights streamed by another producer, and four warps drain TMEM -- all overlapped through mbarriers.
+ * One persistent CTA per SM; per tile of 128 nodes a producer warp stages the distinct neighbour rows of
+ * each 64-node group (64-channel slices of 128 B) in shared memory with cp.async, sixteen warps take the
+ * max from shared memory in registers and write the bf16 A operand, one thread issues the MMAs against
+ * weights streamed through the TMA engine by another producer, and four warps drain TMEM -- all
+ * overlapped through mbarriers.
  * All node-major tensors are in PLAN order.  Co in {64,128,256}; layer.kin == Co; layer.nout <= 512;
- * K <= 40; every tile's distinct-neighbour count <= CP_PLAN_UMAX. */
+ * K <= 32; every group's distinct-neighbour count <= CP_PLAN_UMAX (else use cp_chain_fwd(CP_PRO_AGG)). */
 typedef struct {
   int B, N;
   const void* z; int ld_z; int Co;

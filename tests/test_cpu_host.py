@@ -197,9 +197,10 @@ def test_graph_plan_invariants(ds, objs, N, K):
         assert torch.equal(torch.sort(perm[g])[0], torch.arange(N))
         # same edges: keypoint ids of the plan-order neighbours == the reference's neighbours of that keypoint
         assert torch.equal(perm[g][plan.idx_p[g].long()], idx[g][perm[g]])
-        lidx = plan.lidx[g].long() & 0xFFFF
+        lidx = (plan.lidx[g].long() & 0xFFFF) // 128      # stored as byte offsets of 128-byte row slices
+        assert bool(((plan.lidx[g].long() & 0xFFFF) % 128 == 0).all())
         for t in range(plan.T):
-            n0, n1 = t * 128, min(N, t * 128 + 128)
+            n0, n1 = t * ops.PLAN_GROUP, min(N, (t + 1) * ops.PLAN_GROUP)
             U = int(plan.ucount[g, t])
             ul = plan.ulist[g, t].long()
             assert U == len(torch.unique(plan.idx_p[g, n0:n1]))
@@ -210,7 +211,7 @@ def test_graph_plan_invariants(ds, objs, N, K):
             if plan.KP > K:   # padding repeats a real neighbour
                 assert torch.equal(lidx[n0:n1, K:], lidx[n0:n1, :1].expand(-1, plan.KP - K))
     # locality is the point of the renumbering: far fewer distinct rows per tile than K * 128
-    assert plan.max_unique < 0.2 * 128 * K or N <= 512
+    assert plan.max_unique < 0.3 * ops.PLAN_GROUP * K or N <= 512
 
 
 def test_graph_plan_without_coordinates_keeps_order():

@@ -191,7 +191,7 @@ def test_graph_plan_invariants(ds, objs, N, K):
     plan = ops.GraphPlan(idx.to(torch.int32), p3d)
     G = len(objs)
     # shipped graph_k = 20 fits the staged kernel's buffer; the K = 40 sweep point falls back to direct gathers
-    assert plan.staged == (plan.max_unique <= ops.PLAN_UMAX) and (plan.staged or K > 20), plan.max_unique
+    assert plan.staged == (plan.max_unique <= ops.PLAN_UMAX and K <= ops.PLAN_MAX_K) and (plan.staged or K > 20), plan.max_unique
     perm = plan.perm.long()
     for g in range(G):
         assert torch.equal(torch.sort(perm[g])[0], torch.arange(N))

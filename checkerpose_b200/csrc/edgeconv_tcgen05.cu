@@ -37,7 +37,9 @@ constexpr int A_CHUNKS = 4;
 constexpr int B_STAGE_BYTES = 128 * 128;
 constexpr int B_STAGES = 3;
 constexpr int UMAX = CP_PLAN_UMAX;
-constexpr int STG_BYTES = UMAX * 128;
+constexpr int STG_SLOTS = 4;                 // staging rounds in flight (barrier pairs)
+constexpr int STG_RING_ROWS = 2 * UMAX;      // staging ring capacity in 128-byte row slices (variable-size rounds)
+constexpr int STG_RING_BYTES = STG_RING_ROWS * 128;
 constexpr int KP_MAX = 32;
 constexpr int LIDX_BYTES = TILE_M * KP_MAX * 2;
 constexpr int TBUF_BYTES = 32 * 128;         // per epilogue warp: 32 rows x 64 bf16, transposed for coalesced stores
@@ -49,7 +51,7 @@ static_assert(SUB_M * 2 == TILE_M && NUM_AGG_WARPS * 4 == SUB_M, "one quarter-wa
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_CHUNKS * A_CHUNK_BYTES;
 constexpr int OFF_STG = OFF_B + B_STAGES * B_STAGE_BYTES;
-constexpr int OFF_LIDX = OFF_STG + 2 * STG_BYTES;
+constexpr int OFF_LIDX = OFF_STG + STG_RING_BYTES;
 constexpr int OFF_TBUF = OFF_LIDX + 2 * LIDX_BYTES;
 constexpr int OFF_BIAS = OFF_TBUF + 4 * TBUF_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
@@ -73,7 +75,8 @@ struct EcParams {
 };
 
 struct Bars {
-  uint64_t stg_full[2], stg_empty[2];
+  uint64_t stg_full[STG_SLOTS], stg_empty[STG_SLOTS];
+  uint32_t stg_off[STG_SLOTS];  // byte offset of each in-flight round inside the staging ring
   uint64_t a_full[A_CHUNKS], a_empty[A_CHUNKS];
   uint64_t b_full[B_STAGES], b_empty[B_STAGES];
   uint64_t acc_full, acc_empty;
@@ -151,7 +154,14 @@ __device__ void stage_producer(const EcParams& kp, uint8_t* sm, Bars* bars, int 
   const uint32_t row_bytes = (uint32_t)p.ld_z * 2;
   const int grp = lane >> 3, sub = lane & 7;
   const uint32_t sm_base = smem_u32(sm);
-  uint32_t it = 0;  // staging rounds issued
+  uint32_t it = 0;        // staging rounds issued
+  uint32_t released = 0;  // rounds known to be released by the aggregators (they release in order)
+  uint32_t head = 0;      // next free row of the staging ring
+  uint32_t rnd_start[STG_SLOTS] = {0, 0, 0, 0}, rnd_len[STG_SLOTS] = {0, 0, 0, 0};
+  auto release_upto = [&](uint32_t n) {  // wait until rounds [released, n) have been consumed
+    for (; released < n; ++released)
+      mbar_wait(&bars->stg_empty[released & (STG_SLOTS - 1)], (released / STG_SLOTS) & 1);
+  };
   int ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     int b, t, g;
@@ -173,18 +183,32 @@ __device__ void stage_producer(const EcParams& kp, uint8_t* sm, Bars* bars, int 
       }
     }
     const int lidx_pieces = (rows_valid * pl.KP * 2) >> 4;
+    // the tile's neighbour-offset table reuses the buffer of tile ti-2: every round of that tile must be released
+    if (ti >= 2) release_upto((uint32_t)(ti - 1) * (uint32_t)(kp.KC * 2));
     for (int c = 0; c < kp.KC; ++c) {
 #pragma unroll
       for (int h = 0; h < 2; ++h, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = it >> 1;
-        if (use > 0) mbar_wait(&bars->stg_empty[buf], (use - 1) & 1);
+        const int slot = it & (STG_SLOTS - 1);
+        if (it >= STG_SLOTS) release_upto(it - STG_SLOTS + 1);   // the slot's previous round
+        // variable-size allocation in the staging ring: U[h] rows, contiguous, behind the newest round
+        const uint32_t need = (uint32_t)max(U[h], 1);
+        uint32_t start = head;
+        if (start + need > STG_RING_ROWS) start = 0;
+        for (uint32_t r = released; r < it; ++r) {               // rounds still in flight, oldest first
+          const uint32_t rs = rnd_start[r & (STG_SLOTS - 1)], rl = rnd_len[r & (STG_SLOTS - 1)];
+          if (start < rs + rl && rs < start + need) release_upto(r + 1);
+        }
+        rnd_start[slot] = start;
+        rnd_len[slot] = need;
+        head = start + need;
+        const int buf = slot;
+        if (lane == 0) bars->stg_off[slot] = start * 128u;
         if (c == 0 && h == 0) {  // the tile's local neighbour offsets ride on the first round's barrier
           const uint8_t* ls = reinterpret_cast<const uint8_t*>(pl.lidx + ((size_t)g * pl.N + (size_t)t * TILE_M) * pl.KP);
           const uint32_t ld = sm_base + OFF_LIDX + (ti & 1) * LIDX_BYTES;
           for (int q = lane; q < lidx_pieces; q += 32) cp_async16(ld + q * 16, ls + q * 16);
         }
-        const uint32_t dst = sm_base + OFF_STG + buf * STG_BYTES + sub * 16;
+        const uint32_t dst = sm_base + OFF_STG + start * 128u + sub * 16;
         const uint8_t* src = zb + c * 128;
 #pragma unroll
         for (int q = 0; q < UMAX / 32; ++q) {  // 32 list entries per register of src_off
@@ -197,6 +221,7 @@ __device__ void stage_producer(const EcParams& kp, uint8_t* sm, Bars* bars, int 
             }
           }
         }
+        if (lane == 0) mbar_arrive(&bars->stg_full[buf]);  // release: publishes stg_off[slot]
         cp_async_arrive_noinc(&bars->stg_full[buf]);
       }
     }
@@ -283,16 +308,16 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     for (int c = 0; c < kp.KC; ++c) {
 #pragma unroll
       for (int h = 0; h < 2; ++h, ++it) {
-        const int buf = it & 1;
+        const int buf = it & (STG_SLOTS - 1);
         const int r = h * SUB_M + qw;
         const bool valid = r < rows_valid;
         // own Q slice first: its latency hides behind the barrier waits
         const uint4 q = valid ? ldg_nc_v4(zq + (size_t)r * p.ld_z + c * 64) : make_uint4(0, 0, 0, 0);
-        mbar_wait(&bars->stg_full[buf], (it >> 1) & 1);
+        mbar_wait(&bars->stg_full[buf], (it / STG_SLOTS) & 1);
         if (h == 0 && ti > 0) mbar_wait(&bars->a_empty[c], (ti - 1) & 1);
         uint4 o = make_uint4(0, 0, 0, 0);
         if (valid) {
-          const uint32_t stg = sm_base + OFF_STG + buf * STG_BYTES + sub * 16;
+          const uint32_t stg = sm_base + OFF_STG + bars->stg_off[buf] + sub * 16;
           const uint32_t li = lidx_s + (uint32_t)(r * KP) * 2;
           uint4 m = make_uint4(0, 0, 0, 0);
           for (int k0 = 0; k0 < K; k0 += 8) {
@@ -420,8 +445,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars->stg_full[s], 32);  // every lane of the stage producer arrives when its cp.async landed
+    for (int s = 0; s < STG_SLOTS; ++s) {
+      mbar_init(&bars->stg_full[s], 33);  // every producer lane when its cp.async landed + lane 0's release of stg_off
       mbar_init(&bars->stg_empty[s], NUM_AGG_WARPS);
     }
     for (int c = 0; c < A_CHUNKS; ++c) {

@@ -33,8 +33,8 @@ class ChainParams(C.Structure):
 
 
 class GraphPlanStruct(C.Structure):
-    _fields_ = [("G", c_i32), ("N", c_i32), ("K", c_i32), ("KP", c_i32), ("T", c_i32), ("umax", c_i32),
-                ("ucount", c_vp), ("ulist", c_vp), ("lidx", c_vp)]
+    _fields_ = [("G", c_i32), ("N", c_i32), ("K", c_i32), ("KP", c_i32), ("T", c_i32), ("umax", c_i32), ("max_unique", c_i32),
+                ("ucount", c_vp), ("ulist", c_vp), ("prog", c_vp)]
 
 
 class EdgeConvParams(C.Structure):
@@ -70,6 +70,8 @@ SIGNATURES = {
     "cp_decode_init": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp_decode_refine": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp_permute_rows": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    "cp_graph_plan_kp": (c_i32, [c_i32]),
+    "cp_edgeconv_ring_rows": (c_i32, [c_i32]),
     "cp_graph_plan_build": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cp_edgeconv_fwd": (c_i32, [C.POINTER(EdgeConvParams), c_vp]),
     "cp_correspondences": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),

@@ -3,10 +3,16 @@
 // The reference builds its static kNN graph once per module in __init__ (checkerpose/model/pipeline.py:248,
 // init.py:98) on farthest-point-sampled keypoints, whose order is spatially incoherent by construction: the
 // 20 neighbours of 128 consecutive keypoints touch ~2000 distinct rows.  This routine, run once next to that
-// knn() call, renumbers the keypoints by recursive coordinate bisection so that every tile of 128
-// consecutive nodes is a compact surface patch (its neighbour lists then touch ~240 distinct rows), and
-// precomputes per group of 64 nodes the list of distinct neighbour rows ("ulist", what the kernel stages in shared
-// memory with bulk-async copies) and, per edge, the position of the neighbour in that list ("lidx").
+// knn() call, prepares everything the kernel needs that depends on the graph only:
+//
+//   1. renumbering: recursive coordinate bisection, so that every tile of 128 consecutive nodes is a compact
+//      surface patch (its neighbour lists then touch ~245 distinct rows instead of ~2000);
+//   2. per tile, the list of distinct neighbour rows ("ulist": what the kernel stages in shared memory);
+//   3. per tile, 64 node PAIRS with their "program": neighbouring nodes share most of their neighbours (15 of 20
+//      on the shipped clouds), so a pair is aggregated as  m = max(common rows);  a = max(m, rest of a);
+//      b = max(m, rest of b)  -- 40 - C shared-memory row reads instead of 40.  Pairs are matched greedily by
+//      overlap, sorted, and every 4 consecutive pairs (one warp of the kernel) use the same C (multiple of 4).
+//
 // Pure integer/geometry preprocessing on the host; nothing here is on the per-RoI path.
 #include <algorithm>
 #include <numeric>
@@ -16,8 +22,8 @@
 
 namespace {
 
-constexpr int TILE = 128;            // nodes per MMA tile: RCB boxes are whole tiles above this size
-constexpr int GROUP = CP_PLAN_GROUP;  // nodes per staging group (one distinct-row list each)
+constexpr int TILE = CP_PLAN_TILE;    // nodes per tile of the kernel = nodes per staging list
+constexpr int PAIRS = CP_PLAN_PAIRS;  // pairs per tile
 
 struct Rcb {
   const float* x;  // (3, N) coordinates of one graph
@@ -54,16 +60,33 @@ struct Rcb {
   }
 };
 
+struct Cand {
+  int ov, a, b;
+};
+
 }  // namespace
 
+extern "C" int cp_graph_plan_kp(int K) {
+  static const int sizes[] = {8, 16, 20, 32, 40};
+  for (int s : sizes)
+    if (K >= 1 && K <= s) return s;
+  return -1;
+}
+
 extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, int N, int K, int umax, int32_t* perm,
-                                   int32_t* idx_p, int32_t* ucount, int32_t* ulist, uint16_t* lidx) {
-  CP_REQUIRE(idx && perm && idx_p && ucount && ulist && lidx, CP_E_INVALID, "cp_graph_plan_build: null pointer");
-  CP_REQUIRE(G > 0 && N > 0 && K > 0 && umax > 0 && umax <= 511, CP_E_INVALID, "cp_graph_plan_build: bad sizes G=%d N=%d K=%d umax=%d", G, N, K, umax);
-  const int T = (N + GROUP - 1) / GROUP;
-  const int KP = (K + 7) / 8 * 8;
+                                   int32_t* idx_p, int32_t* ucount, int32_t* ulist, uint16_t* prog) {
+  CP_REQUIRE(idx && perm && idx_p && ucount && ulist && prog, CP_E_INVALID, "cp_graph_plan_build: null pointer");
+  CP_REQUIRE(G > 0 && N > 0 && K > 0 && umax > 0 && umax <= 512 && umax % 64 == 0, CP_E_INVALID,
+             "cp_graph_plan_build: bad sizes G=%d N=%d K=%d umax=%d (umax: multiple of 64, <= 512)", G, N, K, umax);
+  const int KP = cp_graph_plan_kp(K);
+  CP_REQUIRE(KP > 0, CP_E_UNSUPPORTED, "cp_graph_plan_build: K=%d > 40", K);
+  const int T = (N + TILE - 1) / TILE;
+  const int PW = 2 * KP + 8;
+  const int UI = umax / 64;
   int worst = 0;
-  std::vector<int> ids(N), inv(N), stamp(N), local(N);
+  std::vector<int> ids(N), inv(N), stamp(N, -1), local(N), mark(N, 0), cmark(N, 0);
+  int tick = 0;  // unique stamp per use of mark / cmark
+  std::vector<Cand> cand;
   for (int g = 0; g < G; ++g) {
     int32_t* pg = perm + (size_t)g * N;
     if (xyz) {
@@ -85,9 +108,9 @@ extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, 
       }
     std::fill(stamp.begin(), stamp.end(), -1);
     for (int t = 0; t < T; ++t) {
-      int32_t* ul = ulist + ((size_t)g * T + t) * umax;
-      const int n0 = t * GROUP, n1 = std::min(N, n0 + GROUP);
-      // distinct neighbour rows of the tile, ascending (sequential-ish source addresses for the copies)
+      const size_t gt = (size_t)g * T + t;
+      const int n0 = t * TILE, n1 = std::min(N, n0 + TILE), nv = n1 - n0;
+      // ---- distinct neighbour rows of the tile, ascending (sequential-ish source addresses for the copies) ----
       std::vector<int> u;
       for (int i = n0; i < n1; ++i)
         for (int k = 0; k < K; ++k) {
@@ -100,17 +123,84 @@ extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, 
       std::sort(u.begin(), u.end());
       const int U = (int)u.size();
       worst = std::max(worst, U);
-      ucount[(size_t)g * T + t] = U;
-      for (int q = 0; q < U; ++q) {
-        local[u[q]] = q;
-        if (q < umax) ul[q] = u[q];
+      ucount[gt] = U;
+      // kernel-friendly layout: quarter-warp q of the kernel copies list entries q, q+64, q+128, ...
+      int32_t* ul = ulist + gt * umax;
+      for (int q = 0; q < 64; ++q)
+        for (int i = 0; i < UI; ++i) {
+          const int e = i * 64 + q;
+          ul[q * UI + i] = e < U ? u[e] : -1;
+        }
+      for (int e = 0; e < U; ++e) local[u[e]] = e;
+      auto off = [&](int row) { return (uint16_t)(std::min(local[row], umax - 1) * 128); };  // U > umax: plan unusable anyway
+
+      // ---- pair matching: greedy by overlap of the neighbour sets ----
+      cand.clear();
+      for (int a = 0; a < nv; ++a) {
+        ++tick;
+        for (int k = 0; k < K; ++k) mark[ip[(size_t)(n0 + a) * K + k]] = tick;
+        for (int b = a + 1; b < nv; ++b) {
+          int ov = 0;
+          for (int k = 0; k < K; ++k) ov += mark[ip[(size_t)(n0 + b) * K + k]] == tick;
+          cand.push_back({ov, a, b});
+        }
       }
-      for (int q = U; q < umax; ++q) ul[q] = 0;
-      for (int i = n0; i < n1; ++i) {
-        uint16_t* li = lidx + ((size_t)g * N + i) * KP;
-        // byte offset of the staged row slice; lists longer than umax are truncated and the plan is then unusable
-        for (int k = 0; k < K; ++k) li[k] = (uint16_t)(std::min(local[ip[(size_t)i * K + k]], umax - 1) * 128);
-        for (int k = K; k < KP; ++k) li[k] = li[0];  // padding repeats a real neighbour: harmless under max
+      std::stable_sort(cand.begin(), cand.end(), [](const Cand& x, const Cand& y) { return x.ov > y.ov; });
+      std::vector<char> used(TILE, 0);
+      std::vector<Cand> pairs;
+      for (const Cand& c : cand)
+        if (!used[c.a] && !used[c.b]) {
+          used[c.a] = used[c.b] = 1;
+          pairs.push_back(c);
+        }
+      for (int a = 0; a < nv; ++a)
+        if (!used[a]) pairs.push_back({0, a, 255});  // odd node out: no partner
+      while ((int)pairs.size() < PAIRS) pairs.push_back({-1, 255, 255});  // nothing to do (ragged last tile)
+      // pairs arrive sorted by overlap (greedy order); singles and empties last
+      uint16_t* pt = prog + gt * PAIRS * PW;
+      for (int w = 0; w < PAIRS / 4; ++w) {
+        int cmin = KP;
+        for (int q = 0; q < 4; ++q) cmin = std::min(cmin, std::max(pairs[w * 4 + q].ov, 0));
+        const int C = cmin / 4 * 4;  // common rows taken by every pair of this warp
+        for (int q = 0; q < 4; ++q) {
+          const Cand& pr = pairs[w * 4 + q];
+          uint16_t* e = pt + (size_t)(w * 4 + q) * PW;
+          std::fill(e, e + PW, (uint16_t)0);
+          e[2 * KP] = (uint16_t)((pr.a & 255) | ((pr.b & 255) << 8));
+          e[2 * KP + 1] = (uint16_t)C;
+          if (pr.a == 255) continue;  // empty slot: offsets 0 (always a staged row), results discarded
+          const int32_t* na = ip + (size_t)(n0 + pr.a) * K;
+          // a-list: C common rows first, then a's other neighbours, padded with its first entry
+          int na_common = 0, pos = 0;
+          std::vector<int> common;
+          if (pr.b != 255) {
+            const int32_t* nb = ip + (size_t)(n0 + pr.b) * K;
+            ++tick;
+            for (int k = 0; k < K; ++k) mark[nb[k]] = tick;
+            for (int k = 0; k < K && na_common < C; ++k)
+              if (mark[na[k]] == tick) {
+                common.push_back(na[k]);
+                ++na_common;
+              }
+          }
+          // (a warp-uniform C never exceeds the pair's own overlap, so na_common == C for real pairs; a single
+          //  node in a warp with C > 0 cannot happen because singles have overlap 0)
+          ++tick;
+          for (int r : common) cmark[r] = tick;
+          for (int r : common) e[pos++] = off(r);
+          for (int k = 0; k < K; ++k)
+            if (cmark[na[k]] != tick) e[pos++] = off(na[k]);
+          while (pos < KP) e[pos++] = e[0];
+          // b-list: b's neighbours outside the common part, padded with its first entry (or a's when empty)
+          pos = KP;
+          if (pr.b != 255) {
+            const int32_t* nb = ip + (size_t)(n0 + pr.b) * K;
+            for (int k = 0; k < K; ++k)
+              if (cmark[nb[k]] != tick) e[pos++] = off(nb[k]);
+          }
+          const uint16_t padv = pos > KP ? e[KP] : e[0];
+          while (pos < 2 * KP) e[pos++] = padv;
+        }
       }
     }
   }

@@ -285,43 +285,56 @@ def chain_fwd(*, prologue, B, N, layers, out, out_mode, n_valid=0,
 
 
 # --------------------------------------------------------------------- staged EdgeConv (graph plan)
-PLAN_UMAX = 288     # CP_PLAN_UMAX
-PLAN_GROUP = 64     # CP_PLAN_GROUP
-PLAN_MAX_K = 32
+PLAN_UMAX = 512     # CP_PLAN_UMAX
+PLAN_TILE = 128     # CP_PLAN_TILE
+PLAN_PAIRS = 64     # CP_PLAN_PAIRS
+PLAN_MAX_K = 40
 
 
 class GraphPlan:
     """Device-resident result of cp_graph_plan_build for a (G,N,K) kNN table (see the header).  ``perm`` maps plan
-    position -> keypoint id; ``idx_p`` is the neighbour table in plan numbering; ``staged`` tells whether every tile's
-    distinct-neighbour list fits the staged kernel's shared-memory buffer."""
+    position -> keypoint id; ``idx_p`` is the neighbour table in plan numbering; ``ucount`` / ``ulist`` are the distinct
+    neighbour rows of every 128-node tile, ``prog`` the tile's 64 node-pair programs; ``staged`` tells whether every
+    tile's distinct rows fit the staged kernel's shared-memory ring."""
 
     def __init__(self, idx32: torch.Tensor, xyz):
         """idx32 (G,N,K) int32 tensor in keypoint numbering (the plan lives on its device); xyz (G,3,N) or None."""
         G, N, K = idx32.shape
         dev = idx32.device
-        T = (N + PLAN_GROUP - 1) // PLAN_GROUP
-        KP = (K + 7) // 8 * 8
+        T = (N + PLAN_TILE - 1) // PLAN_TILE
+        KP = int(lib.cp_graph_plan_kp(K))
         idx_h = idx32.cpu().contiguous()
         xyz_h = None if xyz is None else xyz.detach().to("cpu", torch.float32).contiguous()
         if xyz_h is not None and tuple(xyz_h.shape) != (G, 3, N):
             raise RuntimeError(f"GraphPlan: keypoints {tuple(xyz_h.shape)} do not match the graph table {(G, N, K)}")
+        self.G, self.N, self.K, self.KP, self.T = G, N, K, KP, T
+        if KP < 0:      # K > 40: no plan-order staging; keep the caller's numbering and the unstaged kernel
+            self.PW = 0
+            self.max_unique = N
+            self.staged, self.identity = False, True
+            self.perm = torch.arange(N, dtype=torch.int32, device=dev).expand(G, N).contiguous()
+            self.idx_p = idx32.contiguous()
+            self.ucount = self.ulist = self.prog = self.struct = None
+            return
+        PW = 2 * KP + 8
         perm = torch.empty((G, N), dtype=torch.int32)
         idx_p = torch.empty((G, N, K), dtype=torch.int32)
         ucount = torch.empty((G, T), dtype=torch.int32)
-        ulist = torch.empty((G, T, PLAN_UMAX), dtype=torch.int32)
-        lidx = torch.empty((G, N, KP), dtype=torch.int16)
+        ulist = torch.empty((G, T, PLAN_PAIRS, PLAN_UMAX // 64), dtype=torch.int32)
+        prog = torch.empty((G, T, PLAN_PAIRS, PW), dtype=torch.int16)
         worst = lib.cp_graph_plan_build(_p(xyz_h), _p(idx_h), G, N, K, PLAN_UMAX, _p(perm), _p(idx_p), _p(ucount), _p(ulist),
-                                        _p(lidx))
+                                        _p(prog))
         check(min(worst, 0), "cp_graph_plan_build")
-        self.G, self.N, self.K, self.KP, self.T = G, N, K, KP, T
+        self.PW = PW
         self.max_unique = int(worst)
-        self.staged = worst <= PLAN_UMAX and K <= PLAN_MAX_K
+        self.ring_rows = int(lib.cp_edgeconv_ring_rows(KP))
+        self.staged = worst <= min(PLAN_UMAX, self.ring_rows)
         self.identity = bool((perm == torch.arange(N, dtype=torch.int32)).all())
         self.perm = perm.to(dev)
         self.idx_p = idx_p.to(dev)
-        self.ucount, self.ulist, self.lidx = ucount.to(dev), ulist.to(dev), lidx.to(dev)
-        self.struct = GraphPlanStruct(G, N, K, KP, T, PLAN_UMAX, self.ucount.data_ptr(), self.ulist.data_ptr(),
-                                      self.lidx.data_ptr())
+        self.ucount, self.ulist, self.prog = ucount.to(dev), ulist.to(dev), prog.to(dev)
+        self.struct = GraphPlanStruct(G, N, K, KP, T, PLAN_UMAX, self.max_unique, self.ucount.data_ptr(), self.ulist.data_ptr(),
+                                      self.prog.data_ptr())
 
 
 def edgeconv_fwd(*, z, plan: GraphPlan, graph_sel, agg_slope, layer, out, out_mode, n_valid=0, a_out=None):

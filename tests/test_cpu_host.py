@@ -179,39 +179,63 @@ def test_bench_reference_arm_contract():
 
 
 # ------------------------------------------------------------------------------------------------ graph plan (host code)
-@pytest.mark.parametrize("ds,objs,N,K", [("lmo", (1,), 4096, 20), ("ycbv", (21,), 512, 20), ("lm", (2, 9), 300, 8), ("lmo", (5,), 1024, 40)])
+@pytest.mark.parametrize("ds,objs,N,K", [("lmo", (1,), 4096, 20), ("ycbv", (21,), 512, 20), ("lm", (2, 9), 300, 8), ("lmo", (5,), 1024, 40),
+                                         ("lmo", (8,), 200, 13)])
 def test_graph_plan_invariants(ds, objs, N, K):
-    """cp_graph_plan_build: the renumbering is a permutation, the plan-order neighbour table and the per-tile
-    staging lists reproduce the reference graph exactly, and FPS clouds fit the staged kernel's buffer."""
+    """cp_graph_plan_build: the renumbering is a permutation, the plan-order neighbour table, the per-tile staging lists
+    and the node-pair programs reproduce the reference graph exactly, and FPS clouds fit the staged kernel's ring."""
     from checkerpose_b200 import ops
     from checkerpose_b200 import synthetic as syn
     from oracle import checkerpose_oracle as orc
     p3d = torch.cat([syn.p3d_normed_tensor(syn.load_fps_xyz(ds, o, N)) for o in objs], dim=0)
     idx = orc.knn(p3d, K)                                   # (G,N,K) int64, keypoint numbering
     plan = ops.GraphPlan(idx.to(torch.int32), p3d)
-    G = len(objs)
-    # shipped graph_k = 20 fits the staged kernel's buffer; the K = 40 sweep point falls back to direct gathers
-    assert plan.staged == (plan.max_unique <= ops.PLAN_UMAX and K <= ops.PLAN_MAX_K) and (plan.staged or K > 20), plan.max_unique
+    G, KP, TILE = len(objs), plan.KP, ops.PLAN_TILE
+    assert KP >= K and KP % 4 == 0 and plan.PW == 2 * KP + 8
+    assert plan.staged == (plan.max_unique <= min(ops.PLAN_UMAX, plan.ring_rows)) and (plan.staged or K > 20), plan.max_unique
     perm = plan.perm.long()
+    saved = total = 0
     for g in range(G):
         assert torch.equal(torch.sort(perm[g])[0], torch.arange(N))
         # same edges: keypoint ids of the plan-order neighbours == the reference's neighbours of that keypoint
         assert torch.equal(perm[g][plan.idx_p[g].long()], idx[g][perm[g]])
-        lidx = (plan.lidx[g].long() & 0xFFFF) // 128      # stored as byte offsets of 128-byte row slices
-        assert bool(((plan.lidx[g].long() & 0xFFFF) % 128 == 0).all())
         for t in range(plan.T):
-            n0, n1 = t * ops.PLAN_GROUP, min(N, (t + 1) * ops.PLAN_GROUP)
+            n0, n1 = t * TILE, min(N, (t + 1) * TILE)
             U = int(plan.ucount[g, t])
-            ul = plan.ulist[g, t].long()
-            assert U == len(torch.unique(plan.idx_p[g, n0:n1]))
+            want_u = torch.unique(plan.idx_p[g, n0:n1].long())
+            assert U == len(want_u)
             if U > ops.PLAN_UMAX:
                 continue   # list truncated: the caller must not use the staged kernel (plan.staged is False)
-            assert torch.equal(ul[:U], torch.unique(plan.idx_p[g, n0:n1].long()))
-            assert torch.equal(ul[lidx[n0:n1, :K]], plan.idx_p[g, n0:n1].long())
-            if plan.KP > K:   # padding repeats a real neighbour
-                assert torch.equal(lidx[n0:n1, K:], lidx[n0:n1, :1].expand(-1, plan.KP - K))
-    # locality is the point of the renumbering: far fewer distinct rows per tile than K * 128
-    assert plan.max_unique < 0.3 * ops.PLAN_GROUP * K or N <= 512
+            ul = plan.ulist[g, t].long().t().reshape(-1)      # entry [q][i] is list position 64 i + q
+            assert torch.equal(ul[:U], want_u) and bool((ul[U:] == -1).all())
+            prog = plan.prog[g, t].long() & 0xFFFF            # (64, PW)
+            assert bool((prog[:, :2 * KP] % 128 == 0).all())
+            rows = ul[(prog[:, :2 * KP] // 128).clamp(max=U - 1)]   # staged row of every program entry
+            a_id, b_id, C = prog[:, 2 * KP] & 255, prog[:, 2 * KP] >> 8, prog[:, 2 * KP + 1]
+            assert bool((C % 4 == 0).all()) and bool((C.view(-1, 4) == C.view(-1, 4)[:, :1]).all())   # uniform per warp
+            seen = []
+            for q in range(ops.PLAN_PAIRS):
+                c = int(C[q])
+                if int(a_id[q]) == 255:
+                    assert int(b_id[q]) == 255
+                    continue
+                na = set(plan.idx_p[g, n0 + int(a_id[q])].tolist())
+                assert set(rows[q, :KP].tolist()) == na              # a-list (with padding) == a's neighbour set
+                seen.append(int(a_id[q]))
+                total += 2 * KP
+                if int(b_id[q]) != 255:
+                    nb = set(plan.idx_p[g, n0 + int(b_id[q])].tolist())
+                    common = set(rows[q, :c].tolist())
+                    assert len(common) == c and common <= nb         # the first C rows of a are shared with b
+                    assert common | set(rows[q, KP:2 * KP - c].tolist()) == nb
+                    seen.append(int(b_id[q]))
+                    saved += c
+            assert sorted(seen) == list(range(n1 - n0))               # every node of the tile exactly once
+    # locality is the point of the renumbering: far fewer distinct rows per tile than K * 128 ...
+    assert plan.max_unique < 0.3 * TILE * K or N <= 512
+    # ... and neighbouring nodes share neighbours: the pair programs skip a good part of the row reads
+    if N >= 1024 and K >= 20:
+        assert saved / total > 0.25, saved / total
 
 
 def test_graph_plan_without_coordinates_keeps_order():

@@ -2,21 +2,25 @@
 //
 // Replaces StaticGraph_module.forward of checkerpose/model/pipeline.py:45-59 (get_graph_feature :27-40 +
 // Conv2d 1x1 + BatchNorm2d + LeakyReLU + max over K) in the factored form of cp_fold_edgeconv, fused with
-// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 22 warps per SM; the unit
-// of work ("round") is one 64-channel slice of one tile of 128 plan-order nodes:
+// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 14 warps per SM (few warps,
+// many registers: the work is bandwidth-bound, not thread-bound); the unit of work ("round") is one 64-channel
+// slice of one tile of 128 plan-order nodes:
 //
-//   warps 0-15  aggregators.  They are their own staging producers: every thread copies its share of the tile's
+//   warps 0-7   aggregators.  They are their own staging producers: every thread copies its share of the tile's
 //               DISTINCT neighbour row slices (plan.ulist, ~245 rows x 128 B instead of 128 x K gathered rows) from
 //               the [P|Q] table into a shared-memory ring with cp.async (LDGSTS), up to LOOKAHEAD rounds ahead of
-//               the round it reduces.  The ring bookkeeping is a pure function of the plan's list lengths, so the 16
+//               the round it reduces.  The ring bookkeeping is a pure function of the plan's list lengths, so the
 //               warps replicate it (a few words of shared memory per warp) and agree on every round's position
-//               without talking to each other.  To reduce, a quarter-warp owns one node PAIR of the plan: it takes
+//               without talking to each other.  To reduce, a quarter-warp owns node PAIRS of the plan: it takes
 //               the max over the rows the two nodes share once, then over the rest of each (40 - C row reads of
 //               128 bits per lane instead of 40), adds the nodes' own Q slices, applies LeakyReLU and writes the
-//               bf16 A operand slice straight into the SWIZZLE_128B layout tcgen05.mma reads;
-//   warps 16-19 epilogue: TMEM -> registers -> bias / LeakyReLU -> bf16 (or fp32 logits) -> global;
-//   warp 20     weight producer: streams the packed weight tiles (16 KB) with cp.async.bulk (TMA engine);
-//   warp 21     one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete.
+//               bf16 A operand slice straight into the SWIZZLE_128B layout tcgen05.mma reads.  A warp takes pair
+//               groups w and 15 - w of the plan's overlap-sorted list, so every warp reads about the same number
+//               of rows per round;
+//   warps 8-11  epilogue (one warp per TMEM lane quarter): TMEM -> registers -> bias / LeakyReLU -> bf16 (or fp32
+//               logits) -> global;
+//   warp 12     weight producer: streams the packed weight tiles (16 KB) with cp.async.bulk (TMA engine);
+//   warp 13     one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete.
 //
 // The aggregation of tile i+1 overlaps the MMAs and the epilogue of tile i; every hand-off is an mbarrier.
 // The kernel is bound by the shared-memory port.
@@ -29,14 +33,16 @@ using namespace sm100;
 namespace {
 
 constexpr int TILE_M = CP_PLAN_TILE;
-constexpr int NUM_AGG_WARPS = 16;            // 64 quarter-warps = the 64 node pairs of a tile
+constexpr int NUM_AGG_WARPS = 8;             // 32 quarter-warps, two node pairs each per round
 constexpr int AGG_THREADS = NUM_AGG_WARPS * 32;
-constexpr int EPI_WARP0 = 16;                // 4 warps; TMEM lane quarter = warp % 4
+constexpr int NUM_QW = NUM_AGG_WARPS * 4;
+constexpr int EPI_WARP0 = 8;                 // TMEM lane quarter = warp % 4; NUM_EPI_WARPS / 4 warps share a quarter's columns
+constexpr int NUM_EPI_WARPS = 4;
 // The SM's warp scheduler favours higher warp ids, and a warp that spins on an mbarrier still competes for issue
 // slots, so the single-thread roles everything else waits on get the highest warp ids.
-constexpr int W_WARP = 20;                   // weight producer (+ TMEM alloc/dealloc)
-constexpr int MMA_WARP = 21;
-constexpr int NUM_WARPS = 22;
+constexpr int W_WARP = EPI_WARP0 + NUM_EPI_WARPS;                   // weight producer (+ TMEM alloc/dealloc)
+constexpr int MMA_WARP = W_WARP + 1;
+constexpr int NUM_WARPS = MMA_WARP + 1;
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int A_BUF_BYTES = TILE_M * 128;    // one K slice of the A operand: 128 rows x 64 bf16
 constexpr int A_BUFS = 3;
@@ -44,18 +50,18 @@ constexpr int B_STAGE_BYTES = 128 * 128;
 constexpr int B_STAGES = 3;
 constexpr int NBAR = 4;                      // staging rounds that may be unreleased at any time
 constexpr int LOOKAHEAD = 2;                 // rounds copied ahead of the one being reduced
-constexpr int UI = CP_PLAN_UMAX / 64;        // list entries per quarter-warp
-constexpr int TBUF_BYTES = 32 * 128;         // per epilogue warp: 32 rows x 64 bf16, transposed for coalesced stores
+constexpr int UI = CP_PLAN_UMAX / NUM_QW;    // list entries per quarter-warp
+constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: 32 rows x 32 bf16, transposed for coalesced stores
 constexpr int BIAS_BYTES = 512 * 4;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_WTILES = 16;
 constexpr int SMEM_BYTES = 227 * 1024;
-static_assert(UI == 8, "the issue path loads a quarter-warp's list entries as two int4");
+static_assert(UI == 16 && NUM_QW == CP_PLAN_LIST_LANES, "the issue path loads a quarter-warp's 16 uint16 list entries as two uint4");
 
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_BUFS * A_BUF_BYTES;
 constexpr int OFF_TBUF = OFF_B + B_STAGES * B_STAGE_BYTES;
-constexpr int OFF_BIAS = OFF_TBUF + 4 * TBUF_BYTES;
+constexpr int OFF_BIAS = OFF_TBUF + NUM_EPI_WARPS * TBUF_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
 constexpr int OFF_WQ = OFF_BAR + 256;                          // per-warp ring bookkeeping
 constexpr int OFF_PROG = OFF_WQ + NUM_AGG_WARPS * 32;
@@ -86,6 +92,7 @@ struct Bars {
   uint64_t b_full[B_STAGES], b_empty[B_STAGES];
   uint64_t acc_full, acc_empty;
   uint32_t tmem_slot;
+  uint32_t bias_blocks;   // bit i: columns [32 i, 32 i + 32) have a non-zero bias (the P half of a [P|Q] layer has none)
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
@@ -135,6 +142,7 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -224,6 +232,13 @@ __device__ __forceinline__ uint4 max_quad(uint4 m, uint32_t stg, uint32_t w0, ui
   return bf8_max3(bf8_max3(m, v0, v1), v2, v3);
 }
 
+__device__ __forceinline__ void load_quad(uint4 (&v)[4], uint32_t stg, uint32_t w0, uint32_t w1) {
+  v[0] = lds128(stg + (w0 & 0xffffu));
+  v[1] = lds128(stg + (w0 >> 16));
+  v[2] = lds128(stg + (w1 & 0xffffu));
+  v[3] = lds128(stg + (w1 >> 16));
+}
+
 __device__ __forceinline__ uint4 finish_node(uint4 m, uint4 q, float slope) {
   const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, qv[4] = {q.x, q.y, q.z, q.w};
   uint32_t ow[4];
@@ -243,7 +258,7 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
   const cp_edgeconv_params& p = kp.p;
   const cp_graph_plan& pl = p.plan;
   const int grp = lane >> 3, sub = lane & 7;
-  const int q = aw * 4 + grp;   // quarter-warp id, 0..63: copies list entries q, q+64, ...
+  const int q = aw * 4 + grp;   // quarter-warp id, 0..31: copies list entries q, q+32, ...
   const int tid = aw * 32 + lane;
   const uint32_t sm_base = smem_u32(sm);
   const uint32_t wq = sm_base + OFF_WQ + aw * (uint32_t)sizeof(WarpQ);
@@ -255,32 +270,48 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
 
   // ---- issue side ----
   uint32_t iss = 0, iss_c = 0, iss_ti = 0;  // next round to copy: index, slice, tile iteration
-  int iss_tile = blockIdx.x;
   uint32_t loaded_ti = 0xffffffffu;         // tile iteration whose list is in roff[]
   uint32_t U_i = 0;
-  uint32_t roff[UI];                        // table byte offsets of this quarter-warp's rows of the tile's list
+  uint32_t rows2[UI / 2];                   // this quarter-warp's rows of the tile's list, two uint16 per word
   const uint8_t* zb_i = nullptr;            // RoI table base + this lane's 16-byte column
   const uint8_t* prog_src = nullptr;
+  // the list of the tile after that one, prefetched (its load latency would otherwise stall the warp at every tile)
+  uint32_t pre_ti = 0xffffffffu, pre_U = 0;
+  uint4 pre_rows[UI / 8];
+  size_t pre_gt = 0;
+  int pre_b = 0;
   uint32_t vh = 0, ph = 0;                  // ring head: virtual and physical row
   uint32_t rel = 0;                         // rounds < rel are known to be released by all warps
   uint32_t it = 0;                          // round being reduced
   uint32_t arrived = 0;                     // rounds < arrived: this warp has signalled that its copies landed
 
+  auto prefetch_list = [&](uint32_t tix) {  // start loading the list of tile iteration tix
+    const int tile = (int)blockIdx.x + (int)tix * (int)gridDim.x;
+    int t, g;
+    tile_coords(kp, tile, pre_b, t, g);
+    pre_gt = (size_t)g * pl.T + t;
+    pre_U = (uint32_t)__ldg(pl.ucount + pre_gt);
+    const uint4* ul = reinterpret_cast<const uint4*>(pl.ulist + (pre_gt * NUM_QW + q) * UI);
+#pragma unroll
+    for (int i = 0; i < UI / 8; ++i) pre_rows[i] = __ldg(ul + i);
+    pre_ti = tix;
+  };
+
   auto try_issue = [&]() -> bool {
     if (iss_c == 0 && loaded_ti != iss_ti) {  // the copies enter a new tile
-      int b, t, g;
-      tile_coords(kp, iss_tile, b, t, g);
-      const size_t gt = (size_t)g * pl.T + t;
-      U_i = (uint32_t)__ldg(pl.ucount + gt);
-      const int4* ul = reinterpret_cast<const int4*>(pl.ulist + (gt * 64 + q) * UI);
-      const int4 r0 = __ldg(ul), r1 = __ldg(ul + 1);
-      roff[0] = (uint32_t)r0.x * row_bytes; roff[1] = (uint32_t)r0.y * row_bytes;
-      roff[2] = (uint32_t)r0.z * row_bytes; roff[3] = (uint32_t)r0.w * row_bytes;
-      roff[4] = (uint32_t)r1.x * row_bytes; roff[5] = (uint32_t)r1.y * row_bytes;
-      roff[6] = (uint32_t)r1.z * row_bytes; roff[7] = (uint32_t)r1.w * row_bytes;
-      zb_i = reinterpret_cast<const uint8_t*>(p.z) + (size_t)b * p.N * row_bytes + sub * 16;
-      prog_src = reinterpret_cast<const uint8_t*>(pl.prog) + gt * PROG_BYTES;
+      if (pre_ti != iss_ti) prefetch_list(iss_ti);
+      U_i = pre_U;
+#pragma unroll
+      for (int i = 0; i < UI / 8; ++i) {
+        rows2[4 * i + 0] = pre_rows[i].x;
+        rows2[4 * i + 1] = pre_rows[i].y;
+        rows2[4 * i + 2] = pre_rows[i].z;
+        rows2[4 * i + 3] = pre_rows[i].w;
+      }
+      zb_i = reinterpret_cast<const uint8_t*>(p.z) + (size_t)pre_b * p.N * row_bytes + sub * 16;
+      prog_src = reinterpret_cast<const uint8_t*>(pl.prog) + pre_gt * PROG_BYTES;
       loaded_ti = iss_ti;
+      if ((int)iss_ti + 1 < my_tiles) prefetch_list(iss_ti + 1);
     }
     const uint32_t U = U_i;
     uint32_t nvh = vh, nph = ph;
@@ -310,7 +341,10 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     const uint8_t* src = zb_i + iss_c * 128;
 #pragma unroll
     for (int i = 0; i < UI; ++i)
-      if ((uint32_t)(i * 64 + q) < U) cp_async16(dst + i * 8192, src + roff[i]);
+      if ((uint32_t)(i * NUM_QW + q) < U) {
+        const uint32_t row = (i & 1) ? (rows2[i >> 1] >> 16) : (rows2[i >> 1] & 0xffffu);
+        cp_async16(dst + i * (NUM_QW * 128), src + row * row_bytes);
+      }
     if (iss_c == 0) {  // the tile's pair programs ride along with its first round
       const uint32_t pd = sm_base + OFF_PROG + (iss_ti & 1) * PROG_BYTES;
       for (int piece = tid; piece < PROG_BYTES / 16; piece += AGG_THREADS) cp_async16(pd + piece * 16, prog_src + piece * 16);
@@ -319,7 +353,6 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     ++iss;
     if (++iss_c == KC) {
       iss_c = 0;
-      iss_tile += gridDim.x;
       ++iss_ti;
     }
     return true;
@@ -353,45 +386,71 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
       }
       mbar_wait(&bars->stg_full[it % NBAR], (it / NBAR) & 1);
 
-      // ---- this quarter-warp's pair; the pair groups rotate over the warps from slice to slice so that every warp
-      //      sees the same mix of cheap (large C) and expensive pairs over a tile ----
-      const uint32_t pair = (((uint32_t)aw + 4 * c) & (NUM_AGG_WARPS - 1)) * 4 + grp;
-      const uint32_t pe = prog_s + pair * (PW * 2);
-      const uint32_t info = lds32(pe + 2 * KP * 2);
-      const int na = info & 255, nb = (info >> 8) & 255;
-      const uint32_t C = info >> 16;   // warp-uniform
-      const uint4 zero4 = make_uint4(0, 0, 0, 0);
-      const uint4 qa = na != 255 ? ldg_nc_v4(zq + (size_t)na * p.ld_z + c * 64) : zero4;
-      const uint4 qb = nb != 255 ? ldg_nc_v4(zq + (size_t)nb * p.ld_z + c * 64) : zero4;
+      // ---- this quarter-warp's two pairs: groups aw and 15 - aw of the overlap-sorted list (cheap + expensive) ----
+      const uint32_t pe0 = prog_s + (uint32_t)(aw * 4 + grp) * (PW * 2);
+      const uint32_t pe1 = prog_s + (uint32_t)((15 - aw) * 4 + grp) * (PW * 2);
+      const uint32_t info0 = lds32(pe0 + 2 * KP * 2), info1 = lds32(pe1 + 2 * KP * 2);
+      const int node[4] = {(int)(info0 & 255), (int)((info0 >> 8) & 255), (int)(info1 & 255), (int)((info1 >> 8) & 255)};
       const uint32_t stg = sm_base + OFF_RING + lds32(wq + 16 + (it % NBAR) * 4) * 128u + sub * 16;
-
-      uint4 acc = make_uint4(NEG_INF2, NEG_INF2, NEG_INF2, NEG_INF2), mc = acc;
+      // own Q slices of the four nodes: issued first, their (HBM / L2) latency hides behind the row reads of both pairs
+      uint4 qv[4];
 #pragma unroll
-      for (int j = 0; j < KCH; ++j) {
-        if ((uint32_t)(4 * j) == C) mc = acc;
-        const uint2 o = lds64(pe + j * 8);
-        acc = max_quad(acc, stg, o.x, o.y);
+      for (int e = 0; e < 4; ++e)
+        qv[e] = node[e] != 255 ? ldg_nc_v4(zq + (size_t)node[e] * p.ld_z + c * 64) : make_uint4(0, 0, 0, 0);
+      if (c == 0 && tile + (int)gridDim.x < kp.num_tiles) {
+        // pull the Q halves of the NEXT tile's rows into L2 (128 rows x Co bf16 = 2 Co lines of 128 B), so that the
+        // loads above find them there one tile later
+        int nb_, nt_, ng_;
+        tile_coords(kp, tile + (int)gridDim.x, nb_, nt_, ng_);
+        const uint8_t* qn = reinterpret_cast<const uint8_t*>(p.z) + ((size_t)nb_ * p.N + (size_t)nt_ * TILE_M) * row_bytes + p.Co * 2;
+        const int lines_per_row = p.Co >> 6;
+        const int rows_next = min(TILE_M, p.N - nt_ * TILE_M);
+        for (int l = tid; l < rows_next * lines_per_row; l += AGG_THREADS)
+          prefetch_l2(qn + (size_t)(l / lines_per_row) * row_bytes + (l % lines_per_row) * 128);
       }
-      if (C == (uint32_t)KP) mc = acc;
-      uint4 accb = mc;
-#pragma unroll
-      for (int j = 0; j < KCH; ++j) {
-        if ((uint32_t)(4 * j) < (uint32_t)KP - C) {
-          const uint2 o = lds64(pe + KP * 2 + j * 8);
-          accb = max_quad(accb, stg, o.x, o.y);
-        }
-      }
-      const uint4 oa = finish_node(acc, qa, slope), ob = finish_node(accb, qb, slope);
-
       const uint32_t ab = it % A_BUFS;
-      if (it >= A_BUFS) mbar_wait(&bars->a_empty[ab], ((it / A_BUFS) - 1) & 1);   // MMAs that read this buffer are done
-      if (na != 255) {
-        sts128(sm_base + a_offset(ab, na, sub), oa);
-        if (aout) *reinterpret_cast<uint4*>(aout + (size_t)na * p.ld_a_out + c * 64) = oa;
-      }
-      if (nb != 255) {
-        sts128(sm_base + a_offset(ab, nb, sub), ob);
-        if (aout) *reinterpret_cast<uint4*>(aout + (size_t)nb * p.ld_a_out + c * 64) = ob;
+
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t pe = pass ? pe1 : pe0;
+        const uint32_t C = (pass ? info1 : info0) >> 16;   // warp-uniform
+        const uint32_t nbch = ((uint32_t)KP - C) >> 2;      // chunks of node b's own rows
+        // all row offsets of the pair first (two uint16 per word), then the rows, software-pipelined: the loads of
+        // chunk j+1 are issued before the maxima of chunk j
+        uint2 oa[KCH], ob[KCH];
+#pragma unroll
+        for (int j = 0; j < KCH; ++j) oa[j] = lds64(pe + j * 8);
+#pragma unroll
+        for (int j = 0; j < KCH; ++j) ob[j] = lds64(pe + KP * 2 + j * 8);
+        uint4 acc = make_uint4(NEG_INF2, NEG_INF2, NEG_INF2, NEG_INF2), mc = acc;
+        uint4 v[2][4];
+        load_quad(v[0], stg, oa[0].x, oa[0].y);
+#pragma unroll
+        for (int j = 0; j < KCH; ++j) {
+          if (j + 1 < KCH) load_quad(v[(j + 1) & 1], stg, oa[j + 1].x, oa[j + 1].y);
+          else if (nbch > 0) load_quad(v[(j + 1) & 1], stg, ob[0].x, ob[0].y);
+          if ((uint32_t)(4 * j) == C) mc = acc;
+          acc = bf8_max3(bf8_max3(acc, v[j & 1][0], v[j & 1][1]), v[j & 1][2], v[j & 1][3]);
+        }
+        if (C == (uint32_t)KP) mc = acc;
+        uint4 accb = mc;
+#pragma unroll
+        for (int j = 0; j < KCH; ++j) {
+          if ((uint32_t)j < nbch) {
+            if (j + 1 < KCH && (uint32_t)(j + 1) < nbch) load_quad(v[(KCH + j + 1) & 1], stg, ob[j + 1].x, ob[j + 1].y);
+            accb = bf8_max3(bf8_max3(accb, v[(KCH + j) & 1][0], v[(KCH + j) & 1][1]), v[(KCH + j) & 1][2], v[(KCH + j) & 1][3]);
+          }
+        }
+        if (pass == 0 && it >= A_BUFS) mbar_wait(&bars->a_empty[ab], ((it / A_BUFS) - 1) & 1);   // MMAs that read this buffer are done
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int nd = node[2 * pass + e];
+          if (nd != 255) {
+            const uint4 o = finish_node(e ? accb : acc, qv[2 * pass + e], slope);
+            sts128(sm_base + a_offset(ab, nd, sub), o);
+            if (aout) *reinterpret_cast<uint4*>(aout + (size_t)nd * p.ld_a_out + c * 64) = o;
+          }
+        }
       }
       fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core's async proxy
       __syncwarp();
@@ -404,17 +463,21 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// epilogue
+// epilogue: warp (q, h) drains TMEM lanes [32 q, 32 q + 32) for every (NUM_EPI_WARPS/4)-th 32-column block
 // ------------------------------------------------------------------------------------------------------
-__device__ void epilogue_warps(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base, int q, int lane) {
+template <bool ACT>
+__device__ void epilogue_warps(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base, int ew, int lane) {
   const cp_edgeconv_params& p = kp.p;
   const cp_chain_layer& L = p.layer;
+  const int q = ew & 3, h = ew >> 2;
   const int row = q * 32 + lane;
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
   const uint32_t sm_base = smem_u32(sm);
-  const uint32_t tbuf = sm_base + OFF_TBUF + q * TBUF_BYTES;
+  const uint32_t tbuf = sm_base + OFF_TBUF + ew * TBUF_BYTES;
   const uint32_t bias_s = sm_base + OFF_BIAS;
-  const bool transposed = (p.out_mode == CP_OUT_BF16) && (kp.npad % 64 == 0);
+  const float slope = L.slope;
+  const bool bf16_out = p.out_mode == CP_OUT_BF16;
+  const uint32_t bias_blocks = bars->bias_blocks;
   int ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     const int b = tile / kp.tiles_per_roi, t = tile - b * kp.tiles_per_roi;
@@ -424,66 +487,67 @@ __device__ void epilogue_warps(const EcParams& kp, uint8_t* sm, Bars* bars, uint
     const size_t grow0 = (size_t)b * p.N + n0;
     mbar_wait(&bars->acc_full, ti & 1);
     tc_fence_after_sync();
-    for (int c0 = 0; c0 < kp.npad; c0 += 32) {
+    for (int c0 = h * 32; c0 < kp.npad; c0 += 32 * (NUM_EPI_WARPS / 4)) {
       uint32_t r[32];
-      if (kp.npad - c0 >= 32) {
+      const int ncols = min(32, kp.npad - c0);   // 16 or 32 (npad is a multiple of 16)
+      if (ncols == 32) {
         tmem_ld32(tbase + (uint32_t)c0, r);
-      } else {  // npad is a multiple of 16
-        uint32_t h[16];
-        tmem_ld16(tbase + (uint32_t)c0, h);
+      } else {
+        uint32_t hh[16];
+        tmem_ld16(tbase + (uint32_t)c0, hh);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) { r[e] = h[e]; r[16 + e] = 0; }
+        for (int e = 0; e < 16; ++e) { r[e] = hh[e]; r[16 + e] = 0; }
       }
       tmem_ld_wait();
       float v[32];
 #pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4) {
-        const uint4 bb = lds128(bias_s + (uint32_t)(c0 + e4 * 4) * 4);  // zero-filled when the layer has no bias
-        const float bv[4] = {__uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
+      for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+      if ((bias_blocks >> (c0 >> 5)) & 1) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float x = __uint_as_float(r[e4 * 4 + e]) + bv[e];
-          if (L.act) x = cp::lrelu(x, L.slope);
-          v[e4 * 4 + e] = x;
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const uint4 bb = lds128(bias_s + (uint32_t)(c0 + e4 * 4) * 4);
+          v[e4 * 4 + 0] += __uint_as_float(bb.x);
+          v[e4 * 4 + 1] += __uint_as_float(bb.y);
+          v[e4 * 4 + 2] += __uint_as_float(bb.z);
+          v[e4 * 4 + 3] += __uint_as_float(bb.w);
         }
       }
-      if (transposed) {
-        // 32 columns = 64 B per row into the warp's 32 x 128 B transposition tile (16-byte chunks XOR-swizzled by row)
-        const int half = (c0 >> 5) & 1;
+      if (ACT) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint4 w = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
-                                     f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
-          sts128(tbuf + lane * 128 + (((half * 4 + e) ^ (lane & 7)) << 4), w);
-        }
-        if (half == 1) {
+        for (int e = 0; e < 32; ++e) v[e] = cp::lrelu(v[e], slope);
+      }
+      if (bf16_out) {
+        if (ncols == 32) {
+          // 32 columns = 64 B per row into the warp's 32 x 64 B transposition tile (16-byte chunks XOR-swizzled by row pair)
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint4 w = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
+                                       f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
+            sts128(tbuf + lane * 64 + ((e ^ sw) << 4), w);
+          }
           __syncwarp();
-          const int rr = lane >> 3, ch = lane & 7;
-          bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + q * 32) * p.ld_out + (c0 - 32) + ch * 8;
+          const int rr = lane >> 2, ch = lane & 3;
+          bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + q * 32) * p.ld_out + c0 + ch * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {  // a quarter-warp stores one full 128-byte line of one row
-            const int lr = i * 4 + rr;
-            const uint4 w = lds128(tbuf + lr * 128 + ((ch ^ (lr & 7)) << 4));
+          for (int i = 0; i < 4; ++i) {  // four lanes store the 64 contiguous bytes (two full sectors) of one row
+            const int lr = i * 8 + rr;
+            const uint4 w = lds128(tbuf + lr * 64 + ((ch ^ ((lr >> 1) & 3)) << 4));
             if (q * 32 + lr < rows_valid) *reinterpret_cast<uint4*>(o + (size_t)lr * p.ld_out) = w;
           }
           __syncwarp();
-        }
-      } else if (row_ok) {
-        const int ncols = min(32, kp.npad - c0);
-        if (p.out_mode == CP_OUT_BF16) {
+        } else if (row_ok) {
           bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + row) * p.ld_out + c0;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (e * 8 < ncols)
-              *reinterpret_cast<uint4*>(o + e * 8) = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
-                                                                f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + (grow0 + row) * p.ld_out;
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (c0 + e < p.n_valid) o[c0 + e] = v[e];
+          for (int e = 0; e < 2; ++e)
+            *reinterpret_cast<uint4*>(o + e * 8) = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
+                                                              f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
         }
+      } else if (row_ok) {
+        float* o = reinterpret_cast<float*>(p.out) + (grow0 + row) * p.ld_out;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c0 + e < p.n_valid) o[c0 + e] = v[e];
       }
     }
     tc_fence_before_sync();
@@ -513,12 +577,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
       mbar_init(&bars->b_empty[s], 1);
     }
     mbar_init(&bars->acc_full, 1);
-    mbar_init(&bars->acc_empty, 4);
+    mbar_init(&bars->acc_empty, NUM_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == W_WARP) tmem_alloc(&bars->tmem_slot, TMEM_COLS);
   for (int i = threadIdx.x; i < BIAS_BYTES / 4; i += NTHREADS)   // bias row (zero-padded) for the epilogue's broadcast loads
     reinterpret_cast<float*>(sm + OFF_BIAS)[i] = (kp.p.layer.bias && i < kp.p.layer.nout) ? kp.p.layer.bias[i] : 0.f;
+  if (warp == 0) {
+    bool nz = false;
+    if (kp.p.layer.bias && lane < 16)
+      for (int e = lane * 32; e < min(lane * 32 + 32, kp.p.layer.nout); ++e) nz |= kp.p.layer.bias[e] != 0.f;
+    const uint32_t m = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0) bars->bias_blocks = m;
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -530,8 +601,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
   } else if (warp == W_WARP) {
     if (lane == 0) weight_producer(kp, sm, bars);
     __syncwarp();
-  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
-    epilogue_warps(kp, sm, bars, tmem_base, warp - EPI_WARP0, lane);
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_WARPS) {
+    if (kp.p.layer.act) epilogue_warps<true>(kp, sm, bars, tmem_base, warp - EPI_WARP0, lane);
+    else epilogue_warps<false>(kp, sm, bars, tmem_base, warp - EPI_WARP0, lane);
   } else if (warp < NUM_AGG_WARPS) {
     aggregator<KCH>(kp, sm, bars, warp, lane);
   }

@@ -74,15 +74,15 @@ extern "C" int cp_graph_plan_kp(int K) {
 }
 
 extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, int N, int K, int umax, int32_t* perm,
-                                   int32_t* idx_p, int32_t* ucount, int32_t* ulist, uint16_t* prog) {
+                                   int32_t* idx_p, int32_t* ucount, uint16_t* ulist, uint16_t* prog) {
   CP_REQUIRE(idx && perm && idx_p && ucount && ulist && prog, CP_E_INVALID, "cp_graph_plan_build: null pointer");
-  CP_REQUIRE(G > 0 && N > 0 && K > 0 && umax > 0 && umax <= 512 && umax % 64 == 0, CP_E_INVALID,
-             "cp_graph_plan_build: bad sizes G=%d N=%d K=%d umax=%d (umax: multiple of 64, <= 512)", G, N, K, umax);
+  CP_REQUIRE(G > 0 && N > 0 && N < 65535 && K > 0 && umax > 0 && umax <= 512 && umax % (4 * CP_PLAN_LIST_LANES) == 0, CP_E_INVALID,
+             "cp_graph_plan_build: bad sizes G=%d N=%d K=%d umax=%d (umax: multiple of 128, <= 512)", G, N, K, umax);
   const int KP = cp_graph_plan_kp(K);
   CP_REQUIRE(KP > 0, CP_E_UNSUPPORTED, "cp_graph_plan_build: K=%d > 40", K);
   const int T = (N + TILE - 1) / TILE;
   const int PW = 2 * KP + 8;
-  const int UI = umax / 64;
+  const int LL = CP_PLAN_LIST_LANES, UI = umax / LL;
   int worst = 0;
   std::vector<int> ids(N), inv(N), stamp(N, -1), local(N), mark(N, 0), cmark(N, 0);
   int tick = 0;  // unique stamp per use of mark / cmark
@@ -124,12 +124,12 @@ extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, 
       const int U = (int)u.size();
       worst = std::max(worst, U);
       ucount[gt] = U;
-      // kernel-friendly layout: quarter-warp q of the kernel copies list entries q, q+64, q+128, ...
-      int32_t* ul = ulist + gt * umax;
-      for (int q = 0; q < 64; ++q)
+      // kernel-friendly layout: quarter-warp q of the kernel copies list entries q, q+32, q+64, ...
+      uint16_t* ul = ulist + gt * umax;
+      for (int q = 0; q < LL; ++q)
         for (int i = 0; i < UI; ++i) {
-          const int e = i * 64 + q;
-          ul[q * UI + i] = e < U ? u[e] : -1;
+          const int e = i * LL + q;
+          ul[q * UI + i] = (uint16_t)(e < U ? u[e] : 0xFFFF);
         }
       for (int e = 0; e < U; ++e) local[u[e]] = e;
       auto off = [&](int row) { return (uint16_t)(std::min(local[row], umax - 1) * 128); };  // U > umax: plan unusable anyway

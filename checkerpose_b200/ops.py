@@ -288,6 +288,7 @@ def chain_fwd(*, prologue, B, N, layers, out, out_mode, n_valid=0,
 PLAN_UMAX = 512     # CP_PLAN_UMAX
 PLAN_TILE = 128     # CP_PLAN_TILE
 PLAN_PAIRS = 64     # CP_PLAN_PAIRS
+PLAN_LIST_LANES = 32  # CP_PLAN_LIST_LANES
 PLAN_MAX_K = 40
 
 
@@ -320,7 +321,7 @@ class GraphPlan:
         perm = torch.empty((G, N), dtype=torch.int32)
         idx_p = torch.empty((G, N, K), dtype=torch.int32)
         ucount = torch.empty((G, T), dtype=torch.int32)
-        ulist = torch.empty((G, T, PLAN_PAIRS, PLAN_UMAX // 64), dtype=torch.int32)
+        ulist = torch.empty((G, T, PLAN_LIST_LANES, PLAN_UMAX // PLAN_LIST_LANES), dtype=torch.int16)
         prog = torch.empty((G, T, PLAN_PAIRS, PW), dtype=torch.int16)
         worst = lib.cp_graph_plan_build(_p(xyz_h), _p(idx_h), G, N, K, PLAN_UMAX, _p(perm), _p(idx_p), _p(ucount), _p(ulist),
                                         _p(prog))

@@ -2,28 +2,29 @@
 //
 // Replaces StaticGraph_module.forward of checkerpose/model/pipeline.py:45-59 (get_graph_feature :27-40 +
 // Conv2d 1x1 + BatchNorm2d + LeakyReLU + max over K) in the factored form of cp_fold_edgeconv, fused with
-// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 14 warps per SM (few warps,
-// many registers: the work is bandwidth-bound, not thread-bound); the unit of work ("round") is one 64-channel
+// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 22 warps per SM; the unit of work ("round") is one 64-channel
 // slice of one tile of 128 plan-order nodes:
 //
-//   warps 0-7   aggregators.  They are their own staging producers: every thread copies its share of the tile's
+//   warps 0-15  aggregators.  They are their own staging producers: every thread copies its share of the tile's
 //               DISTINCT neighbour row slices (plan.ulist, ~245 rows x 128 B instead of 128 x K gathered rows) from
 //               the [P|Q] table into a shared-memory ring with cp.async (LDGSTS), up to LOOKAHEAD rounds ahead of
 //               the round it reduces.  The ring bookkeeping is a pure function of the plan's list lengths, so the
 //               warps replicate it (a few words of shared memory per warp) and agree on every round's position
-//               without talking to each other.  To reduce, a quarter-warp owns node PAIRS of the plan: it takes
+//               without talking to each other.  To reduce, a quarter-warp owns one node PAIR of the plan: it takes
 //               the max over the rows the two nodes share once, then over the rest of each (40 - C row reads of
 //               128 bits per lane instead of 40), adds the nodes' own Q slices, applies LeakyReLU and writes the
-//               bf16 A operand slice straight into the SWIZZLE_128B layout tcgen05.mma reads.  A warp takes pair
-//               groups w and 15 - w of the plan's overlap-sorted list, so every warp reads about the same number
-//               of rows per round;
-//   warps 8-11  epilogue (one warp per TMEM lane quarter): TMEM -> registers -> bias / LeakyReLU -> bf16 (or fp32
-//               logits) -> global;
-//   warp 12     weight producer: streams the packed weight tiles (16 KB) with cp.async.bulk (TMA engine);
-//   warp 13     one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete.
+//               bf16 A operand slice straight into the SWIZZLE_128B layout tcgen05.mma reads.  The plan's
+//               overlap-sorted pair groups rotate over the warps from slice to slice, so every warp reads about
+//               the same number of rows per tile;
+//   warps 16-19 epilogue (one warp per TMEM lane quarter): TMEM -> registers -> bias / LeakyReLU -> bf16 -> a
+//               swizzled shared-memory tile -> global with TMA tensor stores (or fp32 logits with plain stores);
+//   warp 20     weight producer: streams the packed weight tiles (16 KB) with cp.async.bulk (TMA engine);
+//   warp 21     one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete.
 //
 // The aggregation of tile i+1 overlaps the MMAs and the epilogue of tile i; every hand-off is an mbarrier.
 // The kernel is bound by the shared-memory port.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -33,10 +34,10 @@ using namespace sm100;
 namespace {
 
 constexpr int TILE_M = CP_PLAN_TILE;
-constexpr int NUM_AGG_WARPS = 8;             // 32 quarter-warps, two node pairs each per round
+constexpr int NUM_AGG_WARPS = 16;            // 64 quarter-warps = the 64 node pairs of a tile
 constexpr int AGG_THREADS = NUM_AGG_WARPS * 32;
 constexpr int NUM_QW = NUM_AGG_WARPS * 4;
-constexpr int EPI_WARP0 = 8;                 // TMEM lane quarter = warp % 4; NUM_EPI_WARPS / 4 warps share a quarter's columns
+constexpr int EPI_WARP0 = NUM_AGG_WARPS;                 // TMEM lane quarter = warp % 4; NUM_EPI_WARPS / 4 warps share a quarter's columns
 constexpr int NUM_EPI_WARPS = 4;
 // The SM's warp scheduler favours higher warp ids, and a warp that spins on an mbarrier still competes for issue
 // slots, so the single-thread roles everything else waits on get the highest warp ids.
@@ -51,12 +52,12 @@ constexpr int B_STAGES = 3;
 constexpr int NBAR = 4;                      // staging rounds that may be unreleased at any time
 constexpr int LOOKAHEAD = 2;                 // rounds copied ahead of the one being reduced
 constexpr int UI = CP_PLAN_UMAX / NUM_QW;    // list entries per quarter-warp
-constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: 32 rows x 32 bf16, transposed for coalesced stores
+constexpr int TBUF_BYTES = 2 * 32 * 64;      // per epilogue warp: two tiles of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores
 constexpr int BIAS_BYTES = 512 * 4;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_WTILES = 16;
 constexpr int SMEM_BYTES = 227 * 1024;
-static_assert(UI == 16 && NUM_QW == CP_PLAN_LIST_LANES, "the issue path loads a quarter-warp's 16 uint16 list entries as two uint4");
+static_assert(UI == 8 && NUM_QW == CP_PLAN_LIST_LANES, "the issue path loads a quarter-warp's 8 uint16 list entries as one uint4");
 
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_BUFS * A_BUF_BYTES;
@@ -64,7 +65,7 @@ constexpr int OFF_TBUF = OFF_B + B_STAGES * B_STAGE_BYTES;
 constexpr int OFF_BIAS = OFF_TBUF + NUM_EPI_WARPS * TBUF_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
 constexpr int OFF_WQ = OFF_BAR + 256;                          // per-warp ring bookkeeping
-constexpr int OFF_PROG = OFF_WQ + NUM_AGG_WARPS * 32;
+constexpr int OFF_PROG = OFF_WQ + NUM_AGG_WARPS * 96;
 __host__ __device__ constexpr int prog_width(int KCH) { return 8 * KCH + 8; }      // uint16 per pair entry (= 2 KP + 8)
 __host__ __device__ constexpr int prog_bytes(int KCH) { return CP_PLAN_PAIRS * prog_width(KCH) * 2; }
 __host__ __device__ constexpr int off_ring(int KCH) { return (OFF_PROG + 2 * prog_bytes(KCH) + 127) & ~127; }
@@ -83,6 +84,7 @@ struct EcParams {
   int npad;          // nout rounded up to 16
   int num_tiles;     // B * ceil(N / 128)
   int tiles_per_roi;
+  int tma_out;       // bf16 output with nout % 32 == 0: the epilogue stores through the tensor map
   WTile wt[MAX_WTILES];  // order: slice-major, then column block
 };
 
@@ -96,11 +98,19 @@ struct Bars {
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
-struct WarpQ {              // replicated per aggregator warp; indexed by round % NBAR
-  uint32_t vstart[NBAR];    // virtual ring position (rows, monotonically increasing) of the round
-  uint32_t pstart[NBAR];    // physical start row of the round in the ring
+struct WarpQ {              // replicated per aggregator warp
+  uint32_t vstart[NBAR];    // [round % NBAR] virtual ring position (rows, monotonically increasing) of the round
+  uint32_t pstart[NBAR];    // [round % NBAR] physical start row of the round in the ring
+  uint32_t iss, iss_c, iss_ti;       // next round to copy: index, slice, tile iteration
+  uint32_t loaded_ti;                // tile iteration whose list is in the threads' rows2[]
+  uint32_t U_i, b_i, gt_i;           // of that tile: distinct rows, RoI, plan tile (g * T + t)
+  uint32_t pre_ti, pre_U;            // tile iteration (and its row count) whose list is prefetched in pre_rows
+  uint32_t vh, ph;                   // ring head: virtual and physical row
+  uint32_t rel;                      // rounds < rel are known to be released by all warps
+  uint32_t arrived;                  // rounds < arrived: this warp has signalled that its copies landed
+  uint32_t pad[3];
 };
-static_assert(sizeof(WarpQ) == 32, "OFF_PROG layout");
+static_assert(sizeof(WarpQ) == 96, "OFF_PROG layout");
 
 __device__ __forceinline__ uint32_t bf2_max3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r;
@@ -239,13 +249,14 @@ __device__ __forceinline__ void load_quad(uint4 (&v)[4], uint32_t stg, uint32_t 
   v[3] = lds128(stg + (w1 >> 16));
 }
 
-__device__ __forceinline__ uint4 finish_node(uint4 m, uint4 q, float slope) {
+__device__ __forceinline__ uint4 finish_node(uint4 m, uint4 q, float slope, bool fast_lrelu) {
   const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, qv[4] = {q.x, q.y, q.z, q.w};
   uint32_t ow[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const float2 a = bf2_to_f2(mw[e]), d = bf2_to_f2(qv[e]);
-    ow[e] = f2_to_bf2(cp::lrelu(a.x + d.x, slope), cp::lrelu(a.y + d.y, slope));
+    const float x = a.x + d.x, y = a.y + d.y;
+    ow[e] = fast_lrelu ? f2_to_bf2(fmaxf(x, x * slope), fmaxf(y, y * slope)) : f2_to_bf2(cp::lrelu(x, slope), cp::lrelu(y, slope));
   }
   return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
@@ -258,63 +269,54 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
   const cp_edgeconv_params& p = kp.p;
   const cp_graph_plan& pl = p.plan;
   const int grp = lane >> 3, sub = lane & 7;
-  const int q = aw * 4 + grp;   // quarter-warp id, 0..31: copies list entries q, q+32, ...
+  const int q = aw * 4 + grp;   // quarter-warp id, 0..63: copies list entries q, q+64, ...
   const int tid = aw * 32 + lane;
   const uint32_t sm_base = smem_u32(sm);
   const uint32_t wq = sm_base + OFF_WQ + aw * (uint32_t)sizeof(WarpQ);
   const float slope = p.agg_slope;
+  const bool fast_lrelu = slope >= 0.f && slope <= 1.f;   // then lrelu(x) == max(x, slope * x)
   const uint32_t row_bytes = (uint32_t)p.ld_z * 2;
   const uint32_t KC = (uint32_t)kp.KC;
   const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint32_t total = (uint32_t)my_tiles * KC;
 
-  // ---- issue side ----
-  uint32_t iss = 0, iss_c = 0, iss_ti = 0;  // next round to copy: index, slice, tile iteration
-  uint32_t loaded_ti = 0xffffffffu;         // tile iteration whose list is in roff[]
-  uint32_t U_i = 0;
-  uint32_t rows2[UI / 2];                   // this quarter-warp's rows of the tile's list, two uint16 per word
-  const uint8_t* zb_i = nullptr;            // RoI table base + this lane's 16-byte column
-  const uint8_t* prog_src = nullptr;
+  // ---- issue side.  Its warp-uniform bookkeeping lives in shared memory (WarpQ), not in registers: every lane
+  //      executes the same updates (same-value stores), so no intra-warp synchronisation is needed ----
+#define WQ_GET(f) lds32(wq + (uint32_t)offsetof(WarpQ, f))
+#define WQ_SET(f, v) sts32(wq + (uint32_t)offsetof(WarpQ, f), (v))
+  WQ_SET(iss, 0u); WQ_SET(iss_c, 0u); WQ_SET(iss_ti, 0u); WQ_SET(loaded_ti, 0xffffffffu); WQ_SET(U_i, 0u);
+  WQ_SET(b_i, 0u); WQ_SET(gt_i, 0u); WQ_SET(pre_ti, 0xffffffffu); WQ_SET(pre_U, 0u);
+  WQ_SET(vh, 0u); WQ_SET(ph, 0u); WQ_SET(rel, 0u); WQ_SET(arrived, 0u);
+  uint32_t rows2[UI / 2] = {0, 0, 0, 0};    // this quarter-warp's rows of the tile's list, two uint16 per word
   // the list of the tile after that one, prefetched (its load latency would otherwise stall the warp at every tile)
-  uint32_t pre_ti = 0xffffffffu, pre_U = 0;
-  uint4 pre_rows[UI / 8];
-  size_t pre_gt = 0;
-  int pre_b = 0;
-  uint32_t vh = 0, ph = 0;                  // ring head: virtual and physical row
-  uint32_t rel = 0;                         // rounds < rel are known to be released by all warps
+  uint4 pre_rows = make_uint4(0, 0, 0, 0);
   uint32_t it = 0;                          // round being reduced
-  uint32_t arrived = 0;                     // rounds < arrived: this warp has signalled that its copies landed
 
   auto prefetch_list = [&](uint32_t tix) {  // start loading the list of tile iteration tix
-    const int tile = (int)blockIdx.x + (int)tix * (int)gridDim.x;
-    int t, g;
-    tile_coords(kp, tile, pre_b, t, g);
-    pre_gt = (size_t)g * pl.T + t;
-    pre_U = (uint32_t)__ldg(pl.ucount + pre_gt);
-    const uint4* ul = reinterpret_cast<const uint4*>(pl.ulist + (pre_gt * NUM_QW + q) * UI);
-#pragma unroll
-    for (int i = 0; i < UI / 8; ++i) pre_rows[i] = __ldg(ul + i);
-    pre_ti = tix;
+    int b, t, g;
+    tile_coords(kp, (int)blockIdx.x + (int)tix * (int)gridDim.x, b, t, g);
+    const size_t gt = (size_t)g * pl.T + t;
+    WQ_SET(pre_U, (uint32_t)__ldg(pl.ucount + gt));
+    pre_rows = __ldg(reinterpret_cast<const uint4*>(pl.ulist + (gt * NUM_QW + q) * UI));
+    WQ_SET(pre_ti, tix);
   };
 
+  // copy round `iss` into the ring if there is room; false = not now
   auto try_issue = [&]() -> bool {
-    if (iss_c == 0 && loaded_ti != iss_ti) {  // the copies enter a new tile
-      if (pre_ti != iss_ti) prefetch_list(iss_ti);
-      U_i = pre_U;
-#pragma unroll
-      for (int i = 0; i < UI / 8; ++i) {
-        rows2[4 * i + 0] = pre_rows[i].x;
-        rows2[4 * i + 1] = pre_rows[i].y;
-        rows2[4 * i + 2] = pre_rows[i].z;
-        rows2[4 * i + 3] = pre_rows[i].w;
-      }
-      zb_i = reinterpret_cast<const uint8_t*>(p.z) + (size_t)pre_b * p.N * row_bytes + sub * 16;
-      prog_src = reinterpret_cast<const uint8_t*>(pl.prog) + pre_gt * PROG_BYTES;
-      loaded_ti = iss_ti;
+    const uint32_t iss = WQ_GET(iss), iss_c = WQ_GET(iss_c), iss_ti = WQ_GET(iss_ti);
+    if (iss_c == 0 && WQ_GET(loaded_ti) != iss_ti) {  // the copies enter a new tile
+      if (WQ_GET(pre_ti) != iss_ti) prefetch_list(iss_ti);
+      WQ_SET(U_i, WQ_GET(pre_U));
+      rows2[0] = pre_rows.x; rows2[1] = pre_rows.y; rows2[2] = pre_rows.z; rows2[3] = pre_rows.w;
+      int b, t, g;
+      tile_coords(kp, (int)blockIdx.x + (int)iss_ti * (int)gridDim.x, b, t, g);
+      WQ_SET(b_i, (uint32_t)b);
+      WQ_SET(gt_i, (uint32_t)(g * pl.T + t));
+      WQ_SET(loaded_ti, iss_ti);
       if ((int)iss_ti + 1 < my_tiles) prefetch_list(iss_ti + 1);
     }
-    const uint32_t U = U_i;
-    uint32_t nvh = vh, nph = ph;
+    const uint32_t U = WQ_GET(U_i);
+    uint32_t nvh = WQ_GET(vh), nph = WQ_GET(ph);
     if (nph + U > R) {  // a round is contiguous in the ring: skip the tail
       nvh += R - nph;
       nph = 0;
@@ -323,22 +325,24 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     // the tile whose program buffer is overwritten
     int need_rel = (int)iss - NBAR;
     if (iss_c == 0) need_rel = max(need_rel, (int)iss - 2 * (int)KC);
+    uint32_t rel = WQ_GET(rel);
     while (rel < iss) {
       const uint32_t oldest_v = lds32(wq + (rel % NBAR) * 4);
       if (nvh + U - oldest_v <= R && (int)rel > need_rel) break;
-      if (rel >= it) return false;  // we still hold that round ourselves: try again after reducing it
+      if (rel >= it) {  // we still hold that round ourselves: try again after reducing it
+        WQ_SET(rel, rel);
+        return false;
+      }
       mbar_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1);
       ++rel;
     }
-    if (lane == 0) {
-      sts32(wq + (iss % NBAR) * 4, nvh);
-      sts32(wq + 16 + (iss % NBAR) * 4, nph);
-    }
-    __syncwarp();
-    vh = nvh + U;
-    ph = nph + U;
+    WQ_SET(rel, rel);
+    sts32(wq + (iss % NBAR) * 4, nvh);
+    sts32(wq + 16 + (iss % NBAR) * 4, nph);
+    WQ_SET(vh, nvh + U);
+    WQ_SET(ph, nph + U);
     const uint32_t dst = sm_base + OFF_RING + (nph + q) * 128u + sub * 16;
-    const uint8_t* src = zb_i + iss_c * 128;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.z) + (size_t)WQ_GET(b_i) * p.N * row_bytes + sub * 16 + iss_c * 128;
 #pragma unroll
     for (int i = 0; i < UI; ++i)
       if ((uint32_t)(i * NUM_QW + q) < U) {
@@ -347,13 +351,16 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
       }
     if (iss_c == 0) {  // the tile's pair programs ride along with its first round
       const uint32_t pd = sm_base + OFF_PROG + (iss_ti & 1) * PROG_BYTES;
+      const uint8_t* prog_src = reinterpret_cast<const uint8_t*>(pl.prog) + (size_t)WQ_GET(gt_i) * PROG_BYTES;
       for (int piece = tid; piece < PROG_BYTES / 16; piece += AGG_THREADS) cp_async16(pd + piece * 16, prog_src + piece * 16);
     }
     cp_async_commit();
-    ++iss;
-    if (++iss_c == KC) {
-      iss_c = 0;
-      ++iss_ti;
+    WQ_SET(iss, iss + 1);
+    if (iss_c + 1 == KC) {
+      WQ_SET(iss_c, 0u);
+      WQ_SET(iss_ti, iss_ti + 1);
+    } else {
+      WQ_SET(iss_c, iss_c + 1);
     }
     return true;
   };
@@ -362,17 +369,19 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     const int b = tile / kp.tiles_per_roi, t = tile - b * kp.tiles_per_roi;
     const int n0 = t * TILE_M;
-    const size_t row0 = (size_t)b * p.N + n0;
-    const bf16* zq = reinterpret_cast<const bf16*>(p.z) + row0 * p.ld_z + p.Co + sub * 8;  // own Q slices
-    bf16* aout = p.a_out ? reinterpret_cast<bf16*>(p.a_out) + row0 * p.ld_a_out + sub * 8 : nullptr;
+    const uint32_t row0 = (uint32_t)(b * p.N + n0);   // B * N < 2^31 (checked by the host)
     const uint32_t prog_s = sm_base + OFF_PROG + (ti & 1) * PROG_BYTES;
     for (uint32_t c = 0; c < KC; ++c, ++it) {
       // ---- copy ahead ----
-      while (iss < total && iss <= it + LOOKAHEAD)
+      uint32_t iss = WQ_GET(iss);
+      while (iss < total && iss <= it + LOOKAHEAD) {
         if (!try_issue()) break;
+        ++iss;
+      }
       // ---- signal "my copies have landed" one round early, so that warps may drift apart by a round ----
       {
         const uint32_t target = min(it + 2, iss);  // rounds < target
+        const uint32_t arrived = WQ_GET(arrived);
         if (arrived < target) {
           const uint32_t pend = iss - target;      // younger groups that may still be in flight
           if (pend == 0) cp_async_wait<0>();
@@ -381,22 +390,23 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
           __syncwarp();
           if (lane == 0)
             for (uint32_t r = arrived; r < target; ++r) mbar_arrive(&bars->stg_full[r % NBAR]);
-          arrived = target;
+          WQ_SET(arrived, target);
         }
       }
       mbar_wait(&bars->stg_full[it % NBAR], (it / NBAR) & 1);
 
-      // ---- this quarter-warp's two pairs: groups aw and 15 - aw of the overlap-sorted list (cheap + expensive) ----
-      const uint32_t pe0 = prog_s + (uint32_t)(aw * 4 + grp) * (PW * 2);
-      const uint32_t pe1 = prog_s + (uint32_t)((15 - aw) * 4 + grp) * (PW * 2);
-      const uint32_t info0 = lds32(pe0 + 2 * KP * 2), info1 = lds32(pe1 + 2 * KP * 2);
-      const int node[4] = {(int)(info0 & 255), (int)((info0 >> 8) & 255), (int)(info1 & 255), (int)((info1 >> 8) & 255)};
-      const uint32_t stg = sm_base + OFF_RING + lds32(wq + 16 + (it % NBAR) * 4) * 128u + sub * 16;
-      // own Q slices of the four nodes: issued first, their (HBM / L2) latency hides behind the row reads of both pairs
-      uint4 qv[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        qv[e] = node[e] != 255 ? ldg_nc_v4(zq + (size_t)node[e] * p.ld_z + c * 64) : make_uint4(0, 0, 0, 0);
+      // ---- this quarter-warp's pair; the overlap-sorted pair groups rotate over the warps from slice to slice so that
+      //      every warp sees the same mix of cheap (large C) and expensive pairs over a tile ----
+      const uint32_t pair = (((uint32_t)aw + 4 * c) & (NUM_AGG_WARPS - 1)) * 4 + grp;
+      const uint32_t pe = prog_s + pair * (PW * 2);
+      const uint32_t info = lds32(pe + 2 * KP * 2);
+      const int na = info & 255, nb = (info >> 8) & 255;
+      const uint32_t nc4 = info >> 18;              // chunks (of 4 rows) the pair shares        } warp-uniform
+      const uint32_t nr4 = (uint32_t)KCH - nc4;     // chunks of each node's own rows            }
+      // own Q slices: issued first, their (L2) latency hides behind the row reads
+      const bf16* zq = reinterpret_cast<const bf16*>(p.z) + p.Co + c * 64 + sub * 8;
+      const uint4 qa = na != 255 ? ldg_nc_v4(zq + (size_t)(row0 + na) * p.ld_z) : make_uint4(0, 0, 0, 0);
+      const uint4 qb = nb != 255 ? ldg_nc_v4(zq + (size_t)(row0 + nb) * p.ld_z) : make_uint4(0, 0, 0, 0);
       if (c == 0 && tile + (int)gridDim.x < kp.num_tiles) {
         // pull the Q halves of the NEXT tile's rows into L2 (128 rows x Co bf16 = 2 Co lines of 128 B), so that the
         // loads above find them there one tile later
@@ -408,49 +418,33 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
         for (int l = tid; l < rows_next * lines_per_row; l += AGG_THREADS)
           prefetch_l2(qn + (size_t)(l / lines_per_row) * row_bytes + (l % lines_per_row) * 128);
       }
-      const uint32_t ab = it % A_BUFS;
+      const uint32_t stg = sm_base + OFF_RING + lds32(wq + 16 + (it % NBAR) * 4) * 128u + sub * 16;
 
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const uint32_t pe = pass ? pe1 : pe0;
-        const uint32_t C = (pass ? info1 : info0) >> 16;   // warp-uniform
-        const uint32_t nbch = ((uint32_t)KP - C) >> 2;      // chunks of node b's own rows
-        // all row offsets of the pair first (two uint16 per word), then the rows, software-pipelined: the loads of
-        // chunk j+1 are issued before the maxima of chunk j
-        uint2 oa[KCH], ob[KCH];
-#pragma unroll
-        for (int j = 0; j < KCH; ++j) oa[j] = lds64(pe + j * 8);
-#pragma unroll
-        for (int j = 0; j < KCH; ++j) ob[j] = lds64(pe + KP * 2 + j * 8);
-        uint4 acc = make_uint4(NEG_INF2, NEG_INF2, NEG_INF2, NEG_INF2), mc = acc;
-        uint4 v[2][4];
-        load_quad(v[0], stg, oa[0].x, oa[0].y);
-#pragma unroll
-        for (int j = 0; j < KCH; ++j) {
-          if (j + 1 < KCH) load_quad(v[(j + 1) & 1], stg, oa[j + 1].x, oa[j + 1].y);
-          else if (nbch > 0) load_quad(v[(j + 1) & 1], stg, ob[0].x, ob[0].y);
-          if ((uint32_t)(4 * j) == C) mc = acc;
-          acc = bf8_max3(bf8_max3(acc, v[j & 1][0], v[j & 1][1]), v[j & 1][2], v[j & 1][3]);
-        }
-        if (C == (uint32_t)KP) mc = acc;
-        uint4 accb = mc;
-#pragma unroll
-        for (int j = 0; j < KCH; ++j) {
-          if ((uint32_t)j < nbch) {
-            if (j + 1 < KCH && (uint32_t)(j + 1) < nbch) load_quad(v[(KCH + j + 1) & 1], stg, ob[j + 1].x, ob[j + 1].y);
-            accb = bf8_max3(bf8_max3(accb, v[(KCH + j) & 1][0], v[(KCH + j) & 1][1]), v[(KCH + j) & 1][2], v[(KCH + j) & 1][3]);
-          }
-        }
-        if (pass == 0 && it >= A_BUFS) mbar_wait(&bars->a_empty[ab], ((it / A_BUFS) - 1) & 1);   // MMAs that read this buffer are done
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int nd = node[2 * pass + e];
-          if (nd != 255) {
-            const uint4 o = finish_node(e ? accb : acc, qv[2 * pass + e], slope);
-            sts128(sm_base + a_offset(ab, nd, sub), o);
-            if (aout) *reinterpret_cast<uint4*>(aout + (size_t)nd * p.ld_a_out + c * 64) = o;
-          }
-        }
+      uint4 acc = make_uint4(NEG_INF2, NEG_INF2, NEG_INF2, NEG_INF2);
+      uint32_t pa = pe;
+      for (uint32_t j = 0; j < nc4; ++j, pa += 8) {       // rows both nodes need
+        const uint2 o = lds64(pa);
+        acc = max_quad(acc, stg, o.x, o.y);
+      }
+      uint4 accb = acc;
+      uint32_t pb = pe + KP * 2;
+      for (uint32_t j = 0; j < nr4; ++j, pa += 8, pb += 8) {   // the rest of each
+        const uint2 oa = lds64(pa), ob = lds64(pb);
+        acc = max_quad(acc, stg, oa.x, oa.y);
+        accb = max_quad(accb, stg, ob.x, ob.y);
+      }
+
+      const uint32_t ab = it % A_BUFS;
+      if (it >= A_BUFS) mbar_wait(&bars->a_empty[ab], ((it / A_BUFS) - 1) & 1);   // MMAs that read this buffer are done
+      if (na != 255) {
+        const uint4 o = finish_node(acc, qa, slope, fast_lrelu);
+        sts128(sm_base + a_offset(ab, na, sub), o);
+        if (p.a_out) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.a_out) + (size_t)(row0 + na) * p.ld_a_out + c * 64 + sub * 8) = o;
+      }
+      if (nb != 255) {
+        const uint4 o = finish_node(accb, qb, slope, fast_lrelu);
+        sts128(sm_base + a_offset(ab, nb, sub), o);
+        if (p.a_out) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.a_out) + (size_t)(row0 + nb) * p.ld_a_out + c * 64 + sub * 8) = o;
       }
       fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core's async proxy
       __syncwarp();
@@ -463,21 +457,28 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// epilogue: warp (q, h) drains TMEM lanes [32 q, 32 q + 32) for every (NUM_EPI_WARPS/4)-th 32-column block
+// epilogue: warp q drains TMEM lanes [32 q, 32 q + 32), 32 columns at a time
 // ------------------------------------------------------------------------------------------------------
-template <bool ACT>
-__device__ void epilogue_warps(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base, int ew, int lane) {
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+template <bool ACT, bool TMA_OUT>
+__device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, uint8_t* sm, Bars* bars, uint32_t tmem_base, int q, int lane) {
   const cp_edgeconv_params& p = kp.p;
   const cp_chain_layer& L = p.layer;
-  const int q = ew & 3, h = ew >> 2;
   const int row = q * 32 + lane;
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
   const uint32_t sm_base = smem_u32(sm);
-  const uint32_t tbuf = sm_base + OFF_TBUF + ew * TBUF_BYTES;
+  const uint32_t tbuf = sm_base + OFF_TBUF + q * TBUF_BYTES;
   const uint32_t bias_s = sm_base + OFF_BIAS;
   const float slope = L.slope;
-  const bool bf16_out = p.out_mode == CP_OUT_BF16;
   const uint32_t bias_blocks = bars->bias_blocks;
+  const int sw = (lane >> 1) & 3;   // SWIZZLE_64B: 16-byte chunk index ^= bits 1-2 of the row
+  uint32_t blk = 0;                 // TMA tiles written so far (they alternate between the warp's two buffers)
   int ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     const int b = tile / kp.tiles_per_roi, t = tile - b * kp.tiles_per_roi;
@@ -487,10 +488,10 @@ __device__ void epilogue_warps(const EcParams& kp, uint8_t* sm, Bars* bars, uint
     const size_t grow0 = (size_t)b * p.N + n0;
     mbar_wait(&bars->acc_full, ti & 1);
     tc_fence_after_sync();
-    for (int c0 = h * 32; c0 < kp.npad; c0 += 32 * (NUM_EPI_WARPS / 4)) {
+    for (int c0 = 0; c0 < kp.npad; c0 += 32) {
       uint32_t r[32];
       const int ncols = min(32, kp.npad - c0);   // 16 or 32 (npad is a multiple of 16)
-      if (ncols == 32) {
+      if (TMA_OUT || ncols == 32) {
         tmem_ld32(tbase + (uint32_t)c0, r);
       } else {
         uint32_t hh[16];
@@ -516,48 +517,50 @@ __device__ void epilogue_warps(const EcParams& kp, uint8_t* sm, Bars* bars, uint
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = cp::lrelu(v[e], slope);
       }
-      if (bf16_out) {
-        if (ncols == 32) {
-          // 32 columns = 64 B per row into the warp's 32 x 64 B transposition tile (16-byte chunks XOR-swizzled by row pair)
-          const int sw = (lane >> 1) & 3;
+      if (TMA_OUT) {
+        // 32 rows x 64 B tile in the SWIZZLE_64B layout of the tensor map; the TMA engine writes it to
+        // out[b, n0 + 32 q .. +32, c0 .. c0+32) and clips rows beyond N
+        const uint32_t tb = tbuf + (blk & 1) * (TBUF_BYTES / 2);
+        if (lane == 0) bulk_wait_read<1>();   // the store that last read this buffer (two tiles ago) is done with it
+        __syncwarp();
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint4 w = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
-                                       f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
-            sts128(tbuf + lane * 64 + ((e ^ sw) << 4), w);
-          }
-          __syncwarp();
-          const int rr = lane >> 2, ch = lane & 3;
-          bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + q * 32) * p.ld_out + c0 + ch * 8;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {  // four lanes store the 64 contiguous bytes (two full sectors) of one row
-            const int lr = i * 8 + rr;
-            const uint4 w = lds128(tbuf + lr * 64 + ((ch ^ ((lr >> 1) & 3)) << 4));
-            if (q * 32 + lr < rows_valid) *reinterpret_cast<uint4*>(o + (size_t)lr * p.ld_out) = w;
-          }
-          __syncwarp();
-        } else if (row_ok) {
+        for (int e = 0; e < 4; ++e) {
+          const uint4 w = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
+                                     f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
+          sts128(tb + lane * 64 + ((e ^ sw) << 4), w);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && q * 32 < rows_valid) {
+          tma_store_3d(out_map, tb, c0, n0 + q * 32, b);
+          bulk_commit();
+        }
+        ++blk;
+      } else if (row_ok) {
+        if (p.out_mode == CP_OUT_BF16) {
           bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + row) * p.ld_out + c0;
 #pragma unroll
-          for (int e = 0; e < 2; ++e)
-            *reinterpret_cast<uint4*>(o + e * 8) = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
-                                                              f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
-        }
-      } else if (row_ok) {
-        float* o = reinterpret_cast<float*>(p.out) + (grow0 + row) * p.ld_out;
+          for (int e = 0; e < 4; ++e)
+            if (e * 8 < ncols)
+              *reinterpret_cast<uint4*>(o + e * 8) = make_uint4(f2_to_bf2(v[e * 8], v[e * 8 + 1]), f2_to_bf2(v[e * 8 + 2], v[e * 8 + 3]),
+                                                                f2_to_bf2(v[e * 8 + 4], v[e * 8 + 5]), f2_to_bf2(v[e * 8 + 6], v[e * 8 + 7]));
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + (grow0 + row) * p.ld_out;
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (c0 + e < p.n_valid) o[c0 + e] = v[e];
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e < p.n_valid) o[c0 + e] = v[e];
+        }
       }
     }
     tc_fence_before_sync();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars->acc_empty);
   }
+  if (TMA_OUT && lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last stores' reads
 }
 
 template <int KCH>
-__global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_constant__ EcParams kp) {
+__global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_constant__ EcParams kp, const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
@@ -602,8 +605,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
     if (lane == 0) weight_producer(kp, sm, bars);
     __syncwarp();
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_WARPS) {
-    if (kp.p.layer.act) epilogue_warps<true>(kp, sm, bars, tmem_base, warp - EPI_WARP0, lane);
-    else epilogue_warps<false>(kp, sm, bars, tmem_base, warp - EPI_WARP0, lane);
+    const int q = warp - EPI_WARP0;
+    const bool tma_out = kp.tma_out != 0;
+    if (kp.p.layer.act) {
+      if (tma_out) epilogue_warps<true, true>(kp, &out_map, sm, bars, tmem_base, q, lane);
+      else epilogue_warps<true, false>(kp, &out_map, sm, bars, tmem_base, q, lane);
+    } else {
+      if (tma_out) epilogue_warps<false, true>(kp, &out_map, sm, bars, tmem_base, q, lane);
+      else epilogue_warps<false, false>(kp, &out_map, sm, bars, tmem_base, q, lane);
+    }
   } else if (warp < NUM_AGG_WARPS) {
     aggregator<KCH>(kp, sm, bars, warp, lane);
   }
@@ -614,11 +624,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
 }
 
 template <int KCH>
-cudaError_t launch(const EcParams& kp, int grid, cudaStream_t s) {
+cudaError_t launch(const EcParams& kp, const CUtensorMap& map, int grid, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(edgeconv_kernel<KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  edgeconv_kernel<KCH><<<grid, NTHREADS, SMEM_BYTES, s>>>(kp);
+  edgeconv_kernel<KCH><<<grid, NTHREADS, SMEM_BYTES, s>>>(kp, map);
   return cudaSuccess;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
 }
 
 }  // namespace
@@ -643,7 +668,8 @@ extern "C" int cp_edgeconv_fwd(const cp_edgeconv_params* pp, cp_stream_t s) {
   CP_REQUIRE(p.Co == 64 || p.Co == 128 || p.Co == 256, CP_E_UNSUPPORTED, "cp_edgeconv_fwd: Co=%d not in {64,128,256}", p.Co);
   CP_REQUIRE(p.ld_z >= 2 * p.Co && (p.ld_z % 8) == 0 && (reinterpret_cast<uintptr_t>(p.z) & 15) == 0, CP_E_INVALID,
              "cp_edgeconv_fwd: z must be 16-byte aligned with ld_z %% 8 == 0 and ld_z >= 2*Co (ld_z=%d)", p.ld_z);
-  CP_REQUIRE((size_t)p.N * p.ld_z * 2 < (1ull << 32), CP_E_UNSUPPORTED, "cp_edgeconv_fwd: one RoI's table must be < 4 GB");
+  CP_REQUIRE((size_t)p.N * p.ld_z * 2 < (1ull << 32) && (size_t)p.B * p.N < (1ull << 31), CP_E_UNSUPPORTED,
+             "cp_edgeconv_fwd: one RoI's table must be < 4 GB and B * N < 2^31");
   CP_REQUIRE(pl.ucount && pl.ulist && pl.prog && pl.N == p.N && pl.T == (p.N + TILE_M - 1) / TILE_M && pl.G >= 1, CP_E_INVALID,
              "cp_edgeconv_fwd: graph plan does not match N=%d", p.N);
   CP_REQUIRE(pl.K >= 1 && pl.KP == cp_graph_plan_kp(pl.K), CP_E_UNSUPPORTED, "cp_edgeconv_fwd: K=%d / KP=%d not supported", pl.K, pl.KP);
@@ -687,13 +713,28 @@ extern "C" int cp_edgeconv_fwd(const cp_edgeconv_params* pp, cp_stream_t s) {
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
+  // bf16 outputs whose width is a multiple of 32 columns leave through TMA tensor stores: a 3-D map (columns, nodes, RoIs)
+  // with a 32 x 32 box, so that rows beyond N of a ragged last tile are clipped instead of landing in the next RoI
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  kp.tma_out = (p.out_mode == CP_OUT_BF16 && kp.npad % 32 == 0 && kp.npad == L.nout && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
+  if (kp.tma_out) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    CP_REQUIRE(enc, CP_E_CUDA, "cp_edgeconv_fwd: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)kp.npad, (cuuint64_t)p.N, (cuuint64_t)p.B};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.ld_out * 2, (cuuint64_t)p.N * p.ld_out * 2};
+    const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CP_REQUIRE(r == CUDA_SUCCESS, CP_E_CUDA, "cp_edgeconv_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
   cudaError_t e;
   switch (pl.KP) {
-    case 8: e = launch<2>(kp, grid, (cudaStream_t)s); break;
-    case 16: e = launch<4>(kp, grid, (cudaStream_t)s); break;
-    case 20: e = launch<5>(kp, grid, (cudaStream_t)s); break;
-    case 32: e = launch<8>(kp, grid, (cudaStream_t)s); break;
-    default: e = launch<10>(kp, grid, (cudaStream_t)s); break;
+    case 8: e = launch<2>(kp, map, grid, (cudaStream_t)s); break;
+    case 16: e = launch<4>(kp, map, grid, (cudaStream_t)s); break;
+    case 20: e = launch<5>(kp, map, grid, (cudaStream_t)s); break;
+    case 32: e = launch<8>(kp, map, grid, (cudaStream_t)s); break;
+    default: e = launch<10>(kp, map, grid, (cudaStream_t)s); break;
   }
   CP_REQUIRE(e == cudaSuccess, CP_E_CUDA, "cp_edgeconv_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
   CP_CHECK_LAUNCH("cp_edgeconv_fwd");

@@ -124,7 +124,7 @@ extern "C" int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, 
       const int U = (int)u.size();
       worst = std::max(worst, U);
       ucount[gt] = U;
-      // kernel-friendly layout: quarter-warp q of the kernel copies list entries q, q+32, q+64, ...
+      // kernel-friendly layout: quarter-warp q of the kernel copies list entries q, q+64, q+128, ...
       uint16_t* ul = ulist + gt * umax;
       for (int q = 0; q < LL; ++q)
         for (int i = 0; i < UI; ++i) {

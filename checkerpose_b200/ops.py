@@ -288,7 +288,7 @@ def chain_fwd(*, prologue, B, N, layers, out, out_mode, n_valid=0,
 PLAN_UMAX = 512     # CP_PLAN_UMAX
 PLAN_TILE = 128     # CP_PLAN_TILE
 PLAN_PAIRS = 64     # CP_PLAN_PAIRS
-PLAN_LIST_LANES = 32  # CP_PLAN_LIST_LANES
+PLAN_LIST_LANES = 64  # CP_PLAN_LIST_LANES
 PLAN_MAX_K = 40
 
 

@@ -141,7 +141,7 @@ int cp_chain_fwd(const cp_chain_params* p, cp_stream_t s);
  *   out: perm (G,N) int32      perm[g][n'] = original keypoint stored at plan position n'
  *        idx_p (G,N,K) int32   neighbour lists in plan numbering
  *        ucount (G,T) int32    distinct neighbour rows per tile, T = ceil(N/128)
- *        ulist (G,T,32,umax/32) uint16  entry [q][i] = (32 i + q)-th distinct row (ascending), 0xFFFF beyond ucount
+ *        ulist (G,T,64,umax/64) uint16  entry [q][i] = (64 i + q)-th distinct row (ascending), 0xFFFF beyond ucount
  *                              (N < 65535)
  *        prog (G,T,64,PW) uint16, PW = 2 KP + 8, KP = cp_graph_plan_kp(K): per pair
  *              [0,KP)    node a: byte offsets (128 x position in the tile's list) of its neighbours, the C rows it
@@ -156,7 +156,7 @@ int cp_graph_plan_build(const float* xyz, const int32_t* idx, int G, int N, int 
 #define CP_PLAN_TILE 128  /* nodes per tile of cp_edgeconv_fwd */
 #define CP_PLAN_PAIRS 64  /* node pairs per tile */
 #define CP_PLAN_UMAX 512  /* capacity of a tile's distinct-row list */
-#define CP_PLAN_LIST_LANES 32 /* ulist is stored transposed: one row of umax/32 entries per copying quarter-warp */
+#define CP_PLAN_LIST_LANES 64 /* ulist is stored transposed: one row of umax/64 entries per copying quarter-warp */
 /* Rows of 128 B the kernel's staging ring holds for a plan with list length KP (a tile's rows must fit; the
  * kernel keeps up to three slices in flight when they do). */
 int cp_edgeconv_ring_rows(int KP);
@@ -172,11 +172,12 @@ typedef struct { /* DEVICE pointers to the arrays cp_graph_plan_build produced *
 /* StaticGraph_module (pipeline.py:45-59) in the factored form, fused with the GEMM that consumes it:
  *   A[i,:]  = lrelu(max_k z[b, nbr(i,k), :Co] + z[b, i, Co:2Co])       (never leaves the SM)
  *   out     = act(A . W^T + bias)                                       (tcgen05, fp32 accumulate in TMEM)
- * One persistent CTA per SM.  Per tile of 128 nodes and 64-channel slice the eight aggregator warps copy the
+ * One persistent CTA per SM.  Per tile of 128 nodes and 64-channel slice the sixteen aggregator warps copy the
  * tile's distinct neighbour row slices (128 B each) into a shared-memory ring with cp.async, up to two slices
- * ahead of the one they reduce; a quarter-warp takes the max for two node pairs in registers with 128-bit
+ * ahead of the one they reduce; a quarter-warp takes the max for one node pair in registers with 128-bit
  * shared-memory loads and writes the bf16 A operand; one thread issues the MMAs against weights streamed
- * through the TMA engine by another, and eight warps drain TMEM -- all overlapped through mbarriers.
+ * through the TMA engine by another, and four warps drain TMEM into TMA tensor stores -- all overlapped
+ * through mbarriers.
  * All node-major tensors are in PLAN order.  Co in {64,128,256}; layer.kin == Co; layer.nout <= 512;
  * K <= 40; every tile's distinct-row count <= min(umax, cp_edgeconv_ring_rows(KP)) (else use
  * cp_chain_fwd(CP_PRO_AGG)). */

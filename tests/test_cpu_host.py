@@ -206,7 +206,7 @@ def test_graph_plan_invariants(ds, objs, N, K):
             assert U == len(want_u)
             if U > ops.PLAN_UMAX:
                 continue   # list truncated: the caller must not use the staged kernel (plan.staged is False)
-            ul = (plan.ulist[g, t].long() & 0xFFFF).t().reshape(-1)      # entry [q][i] is list position 32 i + q
+            ul = (plan.ulist[g, t].long() & 0xFFFF).t().reshape(-1)      # entry [q][i] is list position 64 i + q
             assert torch.equal(ul[:U], want_u) and bool((ul[U:] == 0xFFFF).all())
             prog = plan.prog[g, t].long() & 0xFFFF            # (64, PW)
             assert bool((prog[:, :2 * KP] % 128 == 0).all())

@@ -2,7 +2,7 @@
 //
 // Replaces StaticGraph_module.forward of checkerpose/model/pipeline.py:45-59 (get_graph_feature :27-40 +
 // Conv2d 1x1 + BatchNorm2d + LeakyReLU + max over K) in the factored form of cp_fold_edgeconv, fused with
-// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 22 warps per SM; the unit of work ("round") is one 64-channel
+// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 28 warps (7 warpgroups) per SM; the unit of work ("round") is one 64-channel
 // slice of one tile of 128 plan-order nodes:
 //
 //   warps 0-15  aggregators.  They are their own staging producers: every thread copies its share of the tile's
@@ -16,10 +16,14 @@
 //               bf16 A operand slice straight into the SWIZZLE_128B layout tcgen05.mma reads.  The plan's
 //               overlap-sorted pair groups rotate over the warps from slice to slice, so every warp reads about
 //               the same number of rows per tile;
-//   warps 16-19 epilogue (one warp per TMEM lane quarter): TMEM -> registers -> bias / LeakyReLU -> bf16 -> a
-//               swizzled shared-memory tile -> global with TMA tensor stores (or fp32 logits with plain stores);
-//   warp 20     weight producer: streams the packed weight tiles (16 KB) with cp.async.bulk (TMA engine);
-//   warp 21     one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete.
+//   warps 16-23 epilogue (two warps per TMEM lane quarter, every second 32-column block each): TMEM -> registers ->
+//               bias / LeakyReLU -> bf16 -> a swizzled shared-memory tile -> global with TMA tensor stores (or fp32
+//               logits with plain stores);
+//   warp 24     weight producer: streams the packed weight tiles (16 KB) with cp.async.bulk (TMA engine);
+//   warp 25     one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete;
+//   warps 26-27 idle (they complete the warpgroup).
+// The register file is re-divided with setmaxnreg: 88 registers per aggregator thread, 64 per epilogue thread, 24 for
+// the control warpgroup (the kernel is launched at 72).
 //
 // The aggregation of tile i+1 overlaps the MMAs and the epilogue of tile i; every hand-off is an mbarrier.
 // The kernel is bound by the shared-memory port.
@@ -38,12 +42,14 @@ constexpr int NUM_AGG_WARPS = 16;            // 64 quarter-warps = the 64 node p
 constexpr int AGG_THREADS = NUM_AGG_WARPS * 32;
 constexpr int NUM_QW = NUM_AGG_WARPS * 4;
 constexpr int EPI_WARP0 = NUM_AGG_WARPS;                 // TMEM lane quarter = warp % 4; NUM_EPI_WARPS / 4 warps share a quarter's columns
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;
 // The SM's warp scheduler favours higher warp ids, and a warp that spins on an mbarrier still competes for issue
 // slots, so the single-thread roles everything else waits on get the highest warp ids.
 constexpr int W_WARP = EPI_WARP0 + NUM_EPI_WARPS;                   // weight producer (+ TMEM alloc/dealloc)
 constexpr int MMA_WARP = W_WARP + 1;
-constexpr int NUM_WARPS = MMA_WARP + 1;
+constexpr int NUM_WARPS = MMA_WARP + 3;         // two idle warps complete the control warpgroup
+constexpr int REGS_AGG = 88, REGS_EPI = 64, REGS_CTRL = 24;   // 16*88 + 8*64 + 4*24 = 28*72
+static_assert(NUM_WARPS % 4 == 0 && NUM_AGG_WARPS * REGS_AGG + NUM_EPI_WARPS * REGS_EPI + 4 * REGS_CTRL <= NUM_WARPS * 72, "register budget");
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int A_BUF_BYTES = TILE_M * 128;    // one K slice of the A operand: 128 rows x 64 bf16
 constexpr int A_BUFS = 3;
@@ -52,7 +58,7 @@ constexpr int B_STAGES = 3;
 constexpr int NBAR = 4;                      // staging rounds that may be unreleased at any time
 constexpr int LOOKAHEAD = 2;                 // rounds copied ahead of the one being reduced
 constexpr int UI = CP_PLAN_UMAX / NUM_QW;    // list entries per quarter-warp
-constexpr int TBUF_BYTES = 2 * 32 * 64;      // per epilogue warp: two tiles of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores
+constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: a tile of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores
 constexpr int BIAS_BYTES = 512 * 4;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_WTILES = 16;
@@ -467,18 +473,18 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 template <bool ACT, bool TMA_OUT>
-__device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, uint8_t* sm, Bars* bars, uint32_t tmem_base, int q, int lane) {
+__device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, uint8_t* sm, Bars* bars, uint32_t tmem_base, int ew, int lane) {
   const cp_edgeconv_params& p = kp.p;
   const cp_chain_layer& L = p.layer;
+  const int q = ew & 3, h = ew >> 2;
   const int row = q * 32 + lane;
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
   const uint32_t sm_base = smem_u32(sm);
-  const uint32_t tbuf = sm_base + OFF_TBUF + q * TBUF_BYTES;
+  const uint32_t tbuf = sm_base + OFF_TBUF + ew * TBUF_BYTES;
   const uint32_t bias_s = sm_base + OFF_BIAS;
   const float slope = L.slope;
   const uint32_t bias_blocks = bars->bias_blocks;
   const int sw = (lane >> 1) & 3;   // SWIZZLE_64B: 16-byte chunk index ^= bits 1-2 of the row
-  uint32_t blk = 0;                 // TMA tiles written so far (they alternate between the warp's two buffers)
   int ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     const int b = tile / kp.tiles_per_roi, t = tile - b * kp.tiles_per_roi;
@@ -488,7 +494,7 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
     const size_t grow0 = (size_t)b * p.N + n0;
     mbar_wait(&bars->acc_full, ti & 1);
     tc_fence_after_sync();
-    for (int c0 = 0; c0 < kp.npad; c0 += 32) {
+    for (int c0 = h * 32; c0 < kp.npad; c0 += 32 * (NUM_EPI_WARPS / 4)) {
       uint32_t r[32];
       const int ncols = min(32, kp.npad - c0);   // 16 or 32 (npad is a multiple of 16)
       if (TMA_OUT || ncols == 32) {
@@ -520,8 +526,8 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
       if (TMA_OUT) {
         // 32 rows x 64 B tile in the SWIZZLE_64B layout of the tensor map; the TMA engine writes it to
         // out[b, n0 + 32 q .. +32, c0 .. c0+32) and clips rows beyond N
-        const uint32_t tb = tbuf + (blk & 1) * (TBUF_BYTES / 2);
-        if (lane == 0) bulk_wait_read<1>();   // the store that last read this buffer (two tiles ago) is done with it
+        const uint32_t tb = tbuf;
+        if (lane == 0) bulk_wait_read<0>();   // the previous store is done reading the buffer
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -535,7 +541,6 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
           tma_store_3d(out_map, tb, c0, n0 + q * 32, b);
           bulk_commit();
         }
-        ++blk;
       } else if (row_ok) {
         if (p.out_mode == CP_OUT_BF16) {
           bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + row) * p.ld_out + c0;
@@ -598,13 +603,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_slot;
 
-  if (warp == MMA_WARP) {
-    if (lane == 0) mma_issuer(kp, sm, bars, tmem_base);
+  if (warp >= W_WARP) {   // control warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+    if (warp == MMA_WARP) {
+      if (lane == 0) mma_issuer(kp, sm, bars, tmem_base);
+    } else if (warp == W_WARP) {
+      if (lane == 0) weight_producer(kp, sm, bars);
+    }
     __syncwarp();
-  } else if (warp == W_WARP) {
-    if (lane == 0) weight_producer(kp, sm, bars);
-    __syncwarp();
-  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + NUM_EPI_WARPS) {
+  } else if (warp >= EPI_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const int q = warp - EPI_WARP0;
     const bool tma_out = kp.tma_out != 0;
     if (kp.p.layer.act) {
@@ -614,7 +622,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
       if (tma_out) epilogue_warps<false, true>(kp, &out_map, sm, bars, tmem_base, q, lane);
       else epilogue_warps<false, false>(kp, &out_map, sm, bars, tmem_base, q, lane);
     }
-  } else if (warp < NUM_AGG_WARPS) {
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_AGG));
     aggregator<KCH>(kp, sm, bars, warp, lane);
   }
 

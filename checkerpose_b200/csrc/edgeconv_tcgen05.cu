@@ -307,8 +307,9 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     WQ_SET(pre_ti, tix);
   };
 
-  // copy round `iss` into the ring if there is room; false = not now
-  auto try_issue = [&]() -> bool {
+  // copy round `iss` into the ring if there is room; false = not now.  Unless `must` (the round is the one this warp
+  // is about to reduce), it does not wait for slower warps to release ring space -- it tries again a round later.
+  auto try_issue = [&](bool must) -> bool {
     const uint32_t iss = WQ_GET(iss), iss_c = WQ_GET(iss_c), iss_ti = WQ_GET(iss_ti);
     if (iss_c == 0 && WQ_GET(loaded_ti) != iss_ti) {  // the copies enter a new tile
       if (WQ_GET(pre_ti) != iss_ti) prefetch_list(iss_ti);
@@ -339,7 +340,12 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
         WQ_SET(rel, rel);
         return false;
       }
-      mbar_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1);
+      if (must) {
+        mbar_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1);
+      } else if (!mbar_try_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1)) {
+        WQ_SET(rel, rel);
+        return false;
+      }
       ++rel;
     }
     WQ_SET(rel, rel);
@@ -381,7 +387,7 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
       // ---- copy ahead ----
       uint32_t iss = WQ_GET(iss);
       while (iss < total && iss <= it + LOOKAHEAD) {
-        if (!try_issue()) break;
+        if (!try_issue(iss == it)) break;
         ++iss;
       }
       // ---- signal "my copies have landed" one round early, so that warps may drift apart by a round ----

@@ -36,10 +36,13 @@ constexpr int KCHUNK = 64;                       // bf16 elements per 128-byte s
 constexpr int A_CHUNK_BYTES = TILE_M * 128;      // 16 KB: 128 rows x 64 bf16
 constexpr int A_CHUNKS = 4;                      // K <= 256 resident at a time
 constexpr int B_STAGE_BYTES = 128 * 128;         // 16 KB: <=128 weight rows x 64 bf16
-constexpr int STAGES = 2;
+constexpr int STAGES = 3;
 constexpr int TMEM_COLS = 256;
 constexpr int MAX_WTILES = 48;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_CHUNKS * A_CHUNK_BYTES + STAGES * B_STAGE_BYTES + 128;
+// two CTAs per SM: 2 x (SMEM_BYTES + 1 KB reserved) must stay within 227 KB, so there is no alignment slack -- the
+// kernel traps if the dynamic shared-memory window is not 1024-byte aligned (it is: windows are 1 KB granular)
+constexpr int SMEM_BYTES = A_CHUNKS * A_CHUNK_BYTES + STAGES * B_STAGE_BYTES + 256;
+static_assert(2 * (SMEM_BYTES + 1024) <= 227 * 1024, "two CTAs per SM");
 
 struct WTile {
   const uint8_t* ptr;
@@ -95,10 +98,20 @@ __device__ __forceinline__ void fill_rows(uint8_t* A, const bf16* src, int ld, i
   const int cpr = C >> 3;  // 16-byte chunks per row
   const int rpi = 32 / cpr;
   const int sub = lane / cpr, chunk = lane - sub * cpr;
-  for (int r = warp * rpi + sub; r < TILE_M; r += NWARPS * rpi) {
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < rows_valid) v = ldg_nc_v4(src + (row0 + r) * ld + chunk * 8);
-    *reinterpret_cast<uint4*>(A + a_offset(chunk >> 3, r, chunk & 7)) = v;
+  // four rows in flight per thread: the loads of a batch are issued before its stores
+  for (int r0 = warp * rpi + sub; r0 < TILE_M; r0 += 4 * NWARPS * rpi) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * NWARPS * rpi;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (r < rows_valid) v[u] = ldg_nc_v4(src + (row0 + r) * ld + chunk * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * NWARPS * rpi;
+      if (r < TILE_M) *reinterpret_cast<uint4*>(A + a_offset(chunk >> 3, r, chunk & 7)) = v[u];
+    }
   }
 }
 
@@ -158,25 +171,43 @@ __device__ __forceinline__ void fill_taps(uint8_t* A, const cp_chain_params& p, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tap = lane >> 3, chunk = lane & 7;
   const bf16* pb = reinterpret_cast<const bf16*>(p.patches) + (size_t)b * p.Hp * p.Wp * 64;
-  for (int r = warp; r < TILE_M; r += NWARPS) {
-    uint4 v = make_uint4(0, 0, 0, 0);
+  // a thread owns rows warp, warp + 8, ...: first all the ids and masks, then all the tap loads, then the stores, so
+  // that the two dependent global-load latencies are paid once per tile instead of once per row
+  constexpr int RPT = TILE_M / NWARPS;
+  int off[RPT];   // element offset of the tap inside the RoI's patch map, -1 = masked / no row
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int r = warp + u * NWARPS;
+    off[u] = -1;
     if (r < rows_valid) {
       const size_t e = (size_t)b * p.N + n0 + r;
-      const float mk = p.mask ? p.mask[e] : 1.f;
-      if (mk != 0.f) {
-        const int yy = (int)(2 * p.y_id[e]) + ((tap & 1) ? p.tap_step : 0);
-        const int xx = (int)(2 * p.x_id[e]) + ((tap & 2) ? p.tap_step : 0);
-        v = ldg_nc_v4(pb + ((size_t)yy * p.Wp + xx) * 64 + chunk * 8);
-      }
+      const float mk = p.mask ? __ldg(p.mask + e) : 1.f;
+      const int yy = (int)(2 * __ldg(p.y_id + e)) + ((tap & 1) ? p.tap_step : 0);
+      const int xx = (int)(2 * __ldg(p.x_id + e)) + ((tap & 2) ? p.tap_step : 0);
+      if (mk != 0.f) off[u] = (yy * p.Wp + xx) * 64 + chunk * 8;
     }
-    *reinterpret_cast<uint4*>(A + a_offset(tap, r, chunk)) = v;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint4 v[RPT / 2];
+#pragma unroll
+    for (int u = 0; u < RPT / 2; ++u) {
+      const int o = off[h * (RPT / 2) + u];
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (o >= 0) v[u] = ldg_nc_v4(pb + o);
+    }
+#pragma unroll
+    for (int u = 0; u < RPT / 2; ++u) {
+      const int r = warp + (h * (RPT / 2) + u) * NWARPS;
+      *reinterpret_cast<uint4*>(A + a_offset(tap, r, chunk)) = v[u];
+    }
   }
 }
 
 // ---- epilogue: TMEM accumulator columns [0, pcols) of this pass -> bias/act -> destination -----------
 enum { EPI_SMEM = 0, EPI_BF16 = 1, EPI_F32 = 2 };
 
-__device__ __forceinline__ void epilogue(uint32_t tmem_base, int pcols, int col0_global, const float* bias, int act,
+__device__ __forceinline__ void epilogue(uint32_t tmem_base, int pcols, int col0_global, const float* bias, int nout_valid, int act,
                                          float slope, int mode, uint8_t* A, void* out, int ld_out, int n_valid,
                                          int64_t row0, int rows_valid) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,13 +219,25 @@ __device__ __forceinline__ void epilogue(uint32_t tmem_base, int pcols, int col0
   for (int ch = half; ch < nch; ch += 2) {
     uint32_t r[16];
     tmem_ld16(tbase + (uint32_t)(ch * 16), r);
-    tmem_ld_wait();
     const int c0 = ch * 16;  // column within the pass
+    float4 bv[4];            // bias of the 16 columns, loaded while the TMEM read is in flight
+#pragma unroll
+    for (int t = 0; t < 4; ++t) bv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) {
+      if (col0_global + c0 + 16 <= nout_valid && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) bv[t] = __ldg(reinterpret_cast<const float4*>(bias + col0_global + c0) + t);
+      } else {
+        float* bs = reinterpret_cast<float*>(bv);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) bs[t] = (col0_global + c0 + t < nout_valid) ? __ldg(bias + col0_global + c0 + t) : 0.f;
+      }
+    }
+    tmem_ld_wait();
     float v[16];
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
-      float x = __uint_as_float(r[t]);
-      if (bias) x += __ldg(bias + col0_global + c0 + t);
+      float x = __uint_as_float(r[t]) + reinterpret_cast<const float*>(bv)[t];
       if (act) x = cp::lrelu(x, slope);
       v[t] = x;
     }
@@ -224,9 +267,10 @@ __device__ __forceinline__ void epilogue(uint32_t tmem_base, int pcols, int col0
 
 template <int PRO>
 __global__ void __launch_bounds__(NTHREADS, 2) chain_kernel(const __grid_constant__ KParams kp) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const cp_chain_params& p = kp.p;
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_raw;
+  if ((smem_u32(base) & 1023u) != 0) __trap();   // SWIZZLE_128B operand tiles need 1024-byte alignment
   Smem sm;
   sm.A = base;
   sm.Bst = base + A_CHUNKS * A_CHUNK_BYTES;
@@ -344,7 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_kernel(const __grid_constan
         int mode;
         if (!last) mode = EPI_SMEM;
         else mode = (p.out_mode == CP_OUT_BF16) ? EPI_BF16 : EPI_F32;
-        epilogue(tmem_base, pcols, col0, L.bias, L.act, L.slope, mode, sm.A, p.out, p.ld_out, p.n_valid, row0, rows_valid);
+        epilogue(tmem_base, pcols, col0, L.bias, L.nout, L.act, L.slope, mode, sm.A, p.out, p.ld_out, p.n_valid, row0, rows_valid);
         tc_fence_before_sync();
         if (mode == EPI_SMEM) fence_proxy_async_smem();
         __syncthreads();

@@ -405,6 +405,10 @@ bool pow2_64_256(int c) { return c == 64 || c == 128 || c == 256; }
 
 }  // namespace
 
+namespace cp {
+bool taps_chain_try(const cp_chain_params& p, cudaStream_t s, int* rc);   // taps_chain_tcgen05.cu
+}
+
 extern "C" int cp_chain_fwd(const cp_chain_params* pp, cp_stream_t s) {
   CP_REQUIRE(pp, CP_E_INVALID, "cp_chain_fwd: null params");
   const cp_chain_params& p = *pp;
@@ -433,6 +437,12 @@ extern "C" int cp_chain_fwd(const cp_chain_params* pp, cp_stream_t s) {
       break;
     default:
       CP_REQUIRE(false, CP_E_INVALID, "cp_chain_fwd: bad prologue %d", p.prologue);
+  }
+  if (p.prologue == CP_PRO_TAPS) {   // the shipped refine-stage shapes run on the warp-specialised kernel
+    bool shapes_ok = true;
+    for (int l = 0; l < p.num_layers; ++l) shapes_ok = shapes_ok && p.layers[l].w_packed && (reinterpret_cast<uintptr_t>(p.layers[l].w_packed) & 15) == 0;
+    int rc = CP_OK;
+    if (shapes_ok && (p.ld_out % 8) == 0 && cp::taps_chain_try(p, (cudaStream_t)s, &rc)) return rc;
   }
   KParams kp;
   kp.p = p;

@@ -1,0 +1,8 @@
+mkdir -p gpurun_out; rm -f gpurun_out/rc.txt
+python __graft_entry__.py > gpurun_out/build.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu --timeout 120 -p no:cacheprovider -x -k "taps_chain or chain" > gpurun_out/t_kernels.log 2>&1; echo "kernels rc=$?" >> gpurun_out/rc.txt
+timeout 900 python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/t_gpu.log 2>&1; echo "gpu tests rc=$?" >> gpurun_out/rc.txt
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/rc.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv python bench.py --profile --steps 2 --warmup 1 > gpurun_out/ncu_launch.log 2>&1; echo "ncu_launch rc=$?" >> gpurun_out/rc.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:taps_chain_kernel -s 1 -c 2 -o gpurun_out/prof_taps python bench.py --profile --steps 1 --warmup 1 > gpurun_out/ncu_taps.log 2>&1; echo "ncu_taps rc=$?" >> gpurun_out/rc.txt
+cat gpurun_out/rc.txt; tail -15 gpurun_out/t_kernels.log; tail -5 gpurun_out/t_gpu.log; cat gpurun_out/bench.log; tail -3 gpurun_out/bench.err

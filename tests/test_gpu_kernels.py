@@ -306,6 +306,40 @@ def test_chain_three_layers(cp):
     assert (got - h).abs().max() < 2e-2 * h.abs().max(), float((got - h).abs().max())
 
 
+@pytest.mark.parametrize("Cg,H,N,B", [(64, 16, 300, 3), (256, 32, 512, 2), (256, 64, 1024, 2)])
+def test_taps_chain_fused(cp, Cg, H, N, B):
+    """K3 (taps_chain_kernel): 4-tap Index2Feat gather x roi mask | graph feature -> Linear+LReLU x2 -> [P|Q] GEMM vs the
+    same maths in float64 with bf16 re-quantisation between layers (pipeline.py:156-163, 278-286)."""
+    ops = cp.ops
+    g = torch.Generator().manual_seed(Cg + H + N)
+    Hp = H + 1
+    patches = _bf16_round(torch.randn(B, Hp, Hp, 64, generator=g))
+    gf = _bf16_round(torch.randn(B, N, Cg, generator=g))
+    x_id = torch.randint(0, H // 2, (B, N), generator=g)
+    y_id = torch.randint(0, H // 2, (B, N), generator=g)
+    mask = (torch.rand(B, N, generator=g) > 0.2).float()
+    dims = ((256, 256 + Cg), (256, 256), (512, 256))
+    ws = [_bf16_round(torch.randn(o, i, generator=g) * (2.0 / i) ** 0.5) for o, i in dims]
+    bs = [torch.randn(o, generator=g) * 0.1 for o, _ in dims]
+    bi = torch.arange(B)[:, None]
+    taps = torch.cat([patches[bi, 2 * y_id + dy, 2 * x_id + dx] for dy, dx in ((0, 0), (2, 0), (0, 2), (2, 2))], dim=-1)
+    h = torch.cat([taps * mask[:, :, None], gf], dim=-1).double()
+    for li, (w, b) in enumerate(zip(ws, bs)):
+        h = h @ w.double().t() + b.double()
+        if li < 2:
+            h = _bf16_round(torch.nn.functional.leaky_relu(h, 0.01).float()).double()
+    layers = [ops.chain_layer(ops.pack_weight(w.cuda()), b.cuda(), w.shape[1], w.shape[0], li < 2, 0.01)
+              for li, (w, b) in enumerate(zip(ws, bs))]
+    out = torch.full((B, N, 512), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.chain_fwd(prologue=ops.PRO_TAPS, B=B, N=N, patches=patches.cuda().to(torch.bfloat16), tap_step=2, x_id=x_id.cuda(),
+                  y_id=y_id.cuda(), mask=mask.cuda(), graph_feat=gf.cuda().to(torch.bfloat16), layers=layers, out=out,
+                  out_mode=ops.OUT_BF16)
+    got = out.cpu().double()
+    assert bool(torch.isfinite(got).all())
+    # one bf16 rounding of the output + one-ulp differences of the re-quantised intermediates
+    assert (got - h).abs().max() < 2e-2 * h.abs().max(), float((got - h).abs().max() / h.abs().max())
+
+
 def test_chain_agg_prologue(cp):
     """AGG prologue (EdgeConv aggregation in registers) + GEMM vs the same maths in float64."""
     ops = cp.ops

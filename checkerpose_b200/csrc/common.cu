@@ -1,6 +1,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace cp {
@@ -10,6 +12,35 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_out_tensor_map(void* map128, void* out, int ncols, int ld_out, int N, int B, const char* who) {
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  EncodeTiledFn enc = encode_tiled_fn();
+  CP_REQUIRE(enc, CP_E_CUDA, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
+  const cuuint64_t dims[3] = {(cuuint64_t)ncols, (cuuint64_t)N, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld_out * 2, (cuuint64_t)N * ld_out * 2};
+  const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+  const CUresult r = enc(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CP_REQUIRE(r == CUDA_SUCCESS, CP_E_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r);
+  return CP_OK;
 }
 }  // namespace cp
 

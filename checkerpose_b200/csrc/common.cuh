@@ -31,6 +31,11 @@ void set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
+// 3-D TMA tensor map (columns, nodes, RoIs) of a bf16 node-major output (B, N, ld_out) with a 32 x 32 box in the
+// SWIZZLE_64B layout: the epilogues store 32-row x 64-byte tiles through it, and rows beyond N of a ragged last tile are
+// clipped instead of landing in the next RoI.  map128 points at 128 bytes (a CUtensorMap).  CP_OK or an error code.
+int make_out_tensor_map(void* map128, void* out, int ncols, int ld_out, int N, int B, const char* who);
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }

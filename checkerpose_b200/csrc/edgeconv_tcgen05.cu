@@ -646,21 +646,6 @@ cudaError_t launch(const EcParams& kp, const CUtensorMap& map, int grid, cudaStr
   return cudaSuccess;
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
 }  // namespace
 
 extern "C" int cp_edgeconv_ring_rows(int KP) {
@@ -734,14 +719,8 @@ extern "C" int cp_edgeconv_fwd(const cp_edgeconv_params* pp, cp_stream_t s) {
   memset(&map, 0, sizeof(map));
   kp.tma_out = (p.out_mode == CP_OUT_BF16 && kp.npad % 32 == 0 && kp.npad == L.nout && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
   if (kp.tma_out) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    CP_REQUIRE(enc, CP_E_CUDA, "cp_edgeconv_fwd: cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[3] = {(cuuint64_t)kp.npad, (cuuint64_t)p.N, (cuuint64_t)p.B};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.ld_out * 2, (cuuint64_t)p.N * p.ld_out * 2};
-    const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
-    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CP_REQUIRE(r == CUDA_SUCCESS, CP_E_CUDA, "cp_edgeconv_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const int rc = cp::make_out_tensor_map(&map, p.out, kp.npad, p.ld_out, p.N, p.B, "cp_edgeconv_fwd");
+    if (rc != CP_OK) return rc;
   }
   cudaError_t e;
   switch (pl.KP) {

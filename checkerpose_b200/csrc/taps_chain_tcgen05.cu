@@ -12,14 +12,17 @@
 //               of the graph-feature row slices straight into 64-channel A-operand chunks (SWIZZLE_128B) of a 4-slot
 //               ring; the taps' addresses of the NEXT tile are computed while the current one is copied;
 //   warps 4-11  epilogue: TMEM -> registers -> + bias (shared memory) -> LeakyReLU -> bf16 -> either the next GEMM's A
-//               operand in shared memory (h0, h1) or global memory (z);
-//   warp 12     weight producer: the 40 packed 16 KB weight tiles of a node tile through the TMA engine, 5-stage ring;
+//               operand in shared memory (h0, h1) or, for z, a swizzled 32 x 32 tile that leaves through a TMA tensor
+//               store (a thread owns a row: direct stores would write 32 half-filled sectors per instruction);
+//   warp 12     weight producer: the 40 packed 16 KB weight tiles of a node tile through the TMA engine, 4-stage ring;
 //   warp 13     one thread issues tcgen05.mma (M=128, N=128, K=16).
 //
 // TMEM holds two accumulators of 256 columns; the GEMM stages of a tile (L0, L1, L2 first half, L2 second half)
 // alternate between them, so the MMAs of a stage overlap the epilogue of the one before wherever the data allows
 // (L2b over L2a's epilogue, the next tile's L0 over L2b's), and the gathers run a tile ahead of both.
 // cp_chain_fwd (chain_tcgen05.cu) dispatches here for the shipped layer shapes and keeps the generic kernel otherwise.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -37,7 +40,8 @@ constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int CHUNK_BYTES = TILE_M * 128;   // 128 rows x 64 bf16
 constexpr int NX = 4;                       // gather ring slots
 constexpr int NH = 4;                       // chunks of h0 / h1 (256 channels)
-constexpr int B_STAGES = 5, B_STAGE_BYTES = 128 * 128;
+constexpr int B_STAGES = 4, B_STAGE_BYTES = 128 * 128;
+constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: a tile of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores
 constexpr int BIAS_FLOATS = 1024;           // 256 + 256 + 512
 constexpr int ACC_COLS = 256;
 constexpr int MAX_WT = 48;
@@ -45,7 +49,8 @@ constexpr int MAX_WT = 48;
 constexpr int OFF_X = 0;
 constexpr int OFF_H = OFF_X + NX * CHUNK_BYTES;
 constexpr int OFF_B = OFF_H + NH * CHUNK_BYTES;
-constexpr int OFF_BIAS = OFF_B + B_STAGES * B_STAGE_BYTES;
+constexpr int OFF_TBUF = OFF_B + B_STAGES * B_STAGE_BYTES;
+constexpr int OFF_BIAS = OFF_TBUF + NUM_E_WARPS * TBUF_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 512;
 static_assert(SMEM_BYTES + 1024 <= 227 * 1024, "shared memory budget");
@@ -251,17 +256,25 @@ __device__ void mma_issuer(const TcParams& kp, uint8_t* sm, Bars* bars, uint32_t
 // ------------------------------------------------------------------------------------------------------
 // epilogue: warp (q = w & 3, half = w >> 2) drains TMEM lanes [32 q, 32 q + 32), every second 32-column block
 // ------------------------------------------------------------------------------------------------------
-__device__ void epilogue_warps(const TcParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base, int ew, int lane) {
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+__device__ void epilogue_warps(const TcParams& kp, const CUtensorMap* out_map, uint8_t* sm, Bars* bars, uint32_t tmem_base, int ew, int lane) {
   const cp_chain_params& p = kp.p;
   const int q = ew & 3, hh = ew >> 2;
   const int row = q * 32 + lane;
   const uint32_t sm_base = smem_u32(sm);
   const uint32_t bias_s = sm_base + OFF_BIAS;
+  const uint32_t tbuf = sm_base + OFF_TBUF + ew * TBUF_BYTES;
+  const int sw = (lane >> 1) & 3;   // SWIZZLE_64B: 16-byte chunk index ^= bits 1-2 of the row
   uint32_t st = 0, hfree = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x) {
     const int b = tile / kp.tiles_per_roi, n0 = (tile - b * kp.tiles_per_roi) * TILE_M;
     const int rows_valid = min(TILE_M, p.N - n0);
-    const size_t grow = (size_t)b * p.N + n0 + row;
     const int nstages = 2 + kp.halves2;
     for (int k = 0; k < nstages; ++k, ++st) {
       const uint32_t slot = st & 1;
@@ -312,10 +325,17 @@ __device__ void epilogue_warps(const TcParams& kp, uint8_t* sm, Bars* bars, uint
           const uint32_t hb = sm_base + OFF_H + (uint32_t)(c0 >> 6) * CHUNK_BYTES;
 #pragma unroll
           for (int e = 0; e < 4; ++e) sts128(hb + chunk_off(row, ((c0 & 63) >> 3) + e), w[e]);
-        } else if (row < rows_valid) {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + grow * p.ld_out + col0 + c0;
+        } else {
+          if (lane == 0) bulk_wait_read0();   // the previous store is done reading the tile
+          __syncwarp();
 #pragma unroll
-          for (int e = 0; e < 4; ++e) *reinterpret_cast<uint4*>(o + e * 8) = w[e];
+          for (int e = 0; e < 4; ++e) sts128(tbuf + lane * 64 + ((e ^ sw) << 4), w[e]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && q * 32 < rows_valid) {
+            tma_store_3d(out_map, tbuf, col0 + c0, n0 + q * 32, b);
+            bulk_commit();
+          }
         }
       }
       tc_fence_before_sync();
@@ -327,9 +347,10 @@ __device__ void epilogue_warps(const TcParams& kp, uint8_t* sm, Bars* bars, uint
       }
     }
   }
+  if (lane == 0) bulk_wait_read0();   // shared memory must outlive the last stores' reads
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) taps_chain_kernel(const __grid_constant__ TcParams kp) {
+__global__ void __launch_bounds__(NTHREADS, 1) taps_chain_kernel(const __grid_constant__ TcParams kp, const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ __align__(1024) uint8_t sm[];
   if ((smem_u32(sm) & 1023u) != 0) __trap();   // SWIZZLE_128B operand tiles need 1024-byte alignment
   Bars* bars = reinterpret_cast<Bars*>(sm + OFF_BAR);
@@ -367,7 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) taps_chain_kernel(const __grid_co
   if (warp < NUM_G_WARPS) {
     gather_warps(kp, sm, bars, warp, lane);
   } else if (warp < E_WARP0 + NUM_E_WARPS) {
-    epilogue_warps(kp, sm, bars, tmem_base, warp - E_WARP0, lane);
+    epilogue_warps(kp, &out_map, sm, bars, tmem_base, warp - E_WARP0, lane);
   } else if (warp == W_WARP) {
     if (lane == 0) weight_producer(kp, sm, bars);
     __syncwarp();
@@ -427,7 +448,10 @@ bool taps_chain_try(const cp_chain_params& p, cudaStream_t s, int* rc) {
     *rc = CP_E_CUDA;
     return true;
   }
-  taps_chain_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(kp);
+  CUtensorMap map;
+  *rc = cp::make_out_tensor_map(&map, p.out, L2.nout, p.ld_out, p.N, p.B, "cp_chain_fwd(TAPS)");
+  if (*rc != CP_OK) return true;
+  taps_chain_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(kp, map);
   e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cp::set_error("cp_chain_fwd(TAPS): CUDA error %d (%s)", (int)e, cudaGetErrorString(e));

@@ -251,4 +251,5 @@ def test_lm_per_sample_graph_matches_single_object_nets():
             if a.dtype == torch.int64:
                 assert torch.equal(a[rows.cuda()], b)
             else:
-                assert torch.allclose(a[rows.cuda()], b, rtol=1e-4, atol=1e-4)
+                # cuDNN may pick different fp32 algorithms for different batch sizes: north_star's 1e-3 relative, not bit-equality
+                assert torch.allclose(a[rows.cuda()], b, rtol=1e-3, atol=1e-3 * float(b.abs().max()))

@@ -73,7 +73,7 @@ struct TcParams {
 struct Bars {
   uint64_t x_full[NX], x_empty[NX];
   uint64_t b_full[B_STAGES], b_empty[B_STAGES];
-  uint64_t h_full, h_free;
+  uint64_t h_full[NH], h_free;   // h_full per 64-channel chunk: the next GEMM starts on chunk 0 while the epilogue writes chunk 1
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
 };
@@ -224,28 +224,30 @@ __device__ void mma_issuer(const TcParams& kp, uint8_t* sm, Bars* bars, uint32_t
     // ---- L1: h0 -> 256 ----
     {
       const uint32_t d = acquire_acc();
-      mbar_wait(&bars->h_full, hcnt & 1);
-      ++hcnt;
-      tc_fence_after_sync();
       for (int c = 0; c < NH; ++c) {
+        mbar_wait(&bars->h_full[c], hcnt & 1);
+        tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(sm + OFF_H + c * CHUNK_BYTES);
         gemm_block(a_addr, d, c != 0);
         gemm_block(a_addr, d + 128, c != 0);
       }
+      ++hcnt;
       mma_commit(&bars->h_free);            // h0 consumed: the epilogue may write h1 over it
       mma_commit(&bars->acc_full[st & 1]);
       ++st;
     }
     // ---- L2: h1 -> 256 (one pass) or 512 (two passes of 256 columns) ----
-    mbar_wait(&bars->h_full, hcnt & 1);
-    ++hcnt;
-    tc_fence_after_sync();
     for (int half = 0; half < kp.halves2; ++half) {
       const uint32_t d = acquire_acc();
       for (int c = 0; c < NH; ++c) {
+        if (half == 0) {
+          mbar_wait(&bars->h_full[c], hcnt & 1);
+          tc_fence_after_sync();
+        }
         const uint32_t a_addr = smem_u32(sm + OFF_H + c * CHUNK_BYTES);
         for (int nb = 0; nb < kp.P2; ++nb) gemm_block(a_addr, d + nb * 128, c != 0);
       }
+      if (half == 0) ++hcnt;
       if (half == kp.halves2 - 1) mma_commit(&bars->h_free);   // h1 consumed: the next tile's h0 may be written
       mma_commit(&bars->acc_full[st & 1]);
       ++st;
@@ -325,6 +327,9 @@ __device__ void epilogue_warps(const TcParams& kp, const CUtensorMap* out_map, u
           const uint32_t hb = sm_base + OFF_H + (uint32_t)(c0 >> 6) * CHUNK_BYTES;
 #pragma unroll
           for (int e = 0; e < 4; ++e) sts128(hb + chunk_off(row, ((c0 & 63) >> 3) + e), w[e]);
+          fence_proxy_async_smem();   // generic-proxy writes of H -> visible to the tensor core's async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->h_full[c0 >> 6]);   // this warp's half of chunk c0 / 64 is in place
         } else {
           if (lane == 0) bulk_wait_read0();   // the previous store is done reading the tile
           __syncwarp();
@@ -339,12 +344,8 @@ __device__ void epilogue_warps(const TcParams& kp, const CUtensorMap* out_map, u
         }
       }
       tc_fence_before_sync();
-      if (k < 2) fence_proxy_async_smem();   // generic-proxy writes of H -> visible to the tensor core's async proxy
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bars->acc_empty[slot]);
-        if (k < 2) mbar_arrive(&bars->h_full);
-      }
+      if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);
     }
   }
   if (lane == 0) bulk_wait_read0();   // shared memory must outlive the last stores' reads
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) taps_chain_kernel(const __grid_co
       mbar_init(&bars->b_full[s], 1);
       mbar_init(&bars->b_empty[s], 1);
     }
-    mbar_init(&bars->h_full, NUM_E_WARPS);
+    for (int c = 0; c < NH; ++c) mbar_init(&bars->h_full[c], NUM_E_WARPS);   // the 8 warps: 4 lane quarters x 2 column halves of the chunk
     mbar_init(&bars->h_free, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->acc_full[s], 1);

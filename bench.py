@@ -11,8 +11,8 @@ NCCL all-gather of the decoded correspondence records per step inside the timed 
 
 Prints ONE JSON line (rank 0).  ``value`` = RoIs/s with inputs resident in HBM; ``e2e`` = the same through
 the public module API from pinned host buffers (H2D of the feature maps + D2H of the records every step);
-``roofline`` = the dominant kernel (fused EdgeConv aggregation + [P|Q] GEMM, chain_kernel<AGG>) timed live
-with CUDA events on its launching stream; ``cpu_baseline`` = the CPU oracle port of the reference head on
+``roofline`` = the dominant kernel (fused EdgeConv aggregation + [P|Q] GEMM, edgeconv_kernel) timed live
+with CUDA events on its launching stream, ``roofline_k3`` = the same for the sampling + pre-graph MLP kernel; ``cpu_baseline`` = the CPU oracle port of the reference head on
 this box's host cores over a bounded sample.  ``--impl reference`` times only that CPU port.
 """
 import argparse
@@ -33,9 +33,11 @@ METRIC = "RoIs/sec (4096-kpt GNN head)"
 UNIT = "RoIs/s"
 NPOINT, GRAPH_K = 4096, 20
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-# `ncu --set full` capture (profiles/); null until a capture of the current kernel exists
-DOMINANT_KERNEL_DRAM_BYTES = None
-DOMINANT_KERNEL_DRAM_SOURCE = None
+# `ncu --set full` capture of this command (profiles/)
+DOMINANT_KERNEL_DRAM_BYTES = 1.096e9 + 1.022e9
+DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r01_d_edgeconv.txt (ncu --set full, launch 0: dram read 1.096 GB + write 1.022 GB)"
+K3_KERNEL_DRAM_BYTES = 0.564e9 + 1.021e9
+K3_KERNEL_DRAM_SOURCE = "profiles/r01_d_taps_chain.txt (ncu --set full, launch 0: dram read 0.564 GB + write 1.021 GB)"
 DATASET, OBJ_ID = "lmo", 1
 
 
@@ -232,9 +234,24 @@ def run_ours(args):
                 "avg_launch_ms": avg_ms, "launches_per_step": len(dom) / args.steps, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": sum(dom) / ms_total if world == 1 else None, "all_gnn_kernels_share_of_step": allchain / ms_total if world == 1 else None}
 
+    # second kernel of north_star's list: K3, 4-tap sampling + pre-graph MLP + first [P|Q] GEMM (stages 1, 2: Cg = 256)
+    k3 = [a.elapsed_time(b) for sig, a, b in log if sig[0] == ops.PRO_TAPS and sig[1] == 512]
+    roof_k3 = None
+    if k3:
+        k3_ms = sum(k3) / len(k3)
+        k3_bytes = B * N * (4 * 64 + 256 + 512) * s_el           # taps + graph feature read, [P|Q] written
+        k3_flops = 2.0 * B * N * (512 * 256 + 256 * 256 + 256 * 512)
+        ach3 = k3_bytes / (k3_ms * 1e-3) / 1e9
+        roof_k3 = {"bound": "hbm", "kernel": "taps_chain_kernel (4-tap gather x mask | graph feature -> MLP x2 -> [P|Q] GEMM)",
+                   "achieved": ach3, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach3 / peak,
+                   "traffic": K3_KERNEL_DRAM_BYTES, "traffic_source": K3_KERNEL_DRAM_SOURCE, "avg_launch_ms": k3_ms,
+                   "launches_per_step": len(k3) / args.steps, "algorithmic_bytes_per_launch": k3_bytes,
+                   "tensor_tflops": k3_flops / (k3_ms * 1e-3) / 1e12,
+                   "share_of_step": sum(k3) / ms_total if world == 1 else None}
+
     if args.profile:   # under ncu: no e2e / CPU legs, numbers printed here are NOT bench values
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": launches, "roofline": roof}))
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": launches, "roofline": roof, "roofline_k3": roof_k3}))
         return
 
     # ---------------- e2e: pinned host buffers -> public API -> host, every step ----------------
@@ -306,7 +323,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "note": "pinned host feature maps -> PoseNet_GNNskip.forward_with_correspondences -> pinned host records; "
                             "next step's H2D overlaps compute on a copy stream"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_k3": roof_k3, "cpu_baseline": cpu_base,
         }))
     if world > 1:
         dist.destroy_process_group()

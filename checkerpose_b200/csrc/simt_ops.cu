@@ -28,8 +28,44 @@ __global__ void transpose_kernel(const TS* __restrict__ src, TD* __restrict__ ds
   }
 }
 
+// bf16 -> bf16 with R and S multiples of 64 (NCHW <-> NHWC of the HRNet maps, (B,hw,N) -> (B,N,hw) of the init head):
+// 64 x 64 tiles, 128-bit global accesses on both sides (a 128-byte line per 8 threads), transposition through a
+// shared-memory tile of bf16 pairs with an odd row stride (conflict-free in both directions).
+__global__ void __launch_bounds__(256) transpose_bf16_64_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int R, int S) {
+  __shared__ uint32_t tile[64][33];   // [r][pair of s]
+  const int b = blockIdx.z;
+  const int s0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const uint16_t* sb = src + (size_t)b * R * S;
+  uint16_t* db = dst + (size_t)b * R * S;
+  const int t = threadIdx.x, v = t & 7, row = t >> 3;   // 8 threads x 16 B per 128-byte row, 32 rows per pass
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = row + 32 * h;
+    const uint4 x = *reinterpret_cast<const uint4*>(sb + (size_t)(r0 + r) * S + s0 + v * 8);
+    tile[r][v * 4 + 0] = x.x; tile[r][v * 4 + 1] = x.y; tile[r][v * 4 + 2] = x.z; tile[r][v * 4 + 3] = x.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int sidx = row + 32 * h;   // output row = source column
+    const int sel = (sidx & 1) ? 0x7632 : 0x5410;   // take the high / low halves of two words
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t a = tile[v * 8 + 2 * j][sidx >> 1], c = tile[v * 8 + 2 * j + 1][sidx >> 1];
+      w[j] = __byte_perm(a, c, sel);
+    }
+    *reinterpret_cast<uint4*>(db + (size_t)(s0 + sidx) * R + r0 + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 template <typename TS, typename TD>
 int launch_transpose(const void* src, void* dst, int B, int R, int S, cudaStream_t st) {
+  if (sizeof(TS) == 2 && sizeof(TD) == 2 && R % 64 == 0 && S % 64 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    dim3 grid(S / 64, R / 64, B);
+    transpose_bf16_64_kernel<<<grid, 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, R, S);
+    return 0;
+  }
   dim3 grid(cp::ceil_div(S, 32), cp::ceil_div(R, 32), B), block(32, 8);
   transpose_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)src, (TD*)dst, R, S);
   return 0;

@@ -235,7 +235,12 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
             x0 = conv(feat_last.to(torch.bfloat16))
         else:
             x0 = init_net.conv1x1(feat_last.float())
-    x = x0.contiguous().view(B, N, 64)  # == out.view(-1, N, 64): channel = 8x8 cell (init.py:114)
+    # == out.view(-1, N, 64): channel = 8x8 cell (init.py:114)
+    hw = x0.shape[2] * x0.shape[3]
+    if dtype == torch.bfloat16 and x0.is_contiguous(memory_format=torch.channels_last) and not x0.is_contiguous():
+        x = ops.to_channel_major(x0.permute(0, 2, 3, 1).reshape(B, hw, N), torch.bfloat16)   # (B,hw,N) -> (B,N,hw), tiled transpose
+    else:
+        x = x0.contiguous().view(B, N, hw)
     blocks = list(init_net.pre_query_block)
     mlp = prepared_linear(init_net.mlp, dtype)
     nbits = mlp.nout
@@ -274,6 +279,18 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
 # --------------------------------------------------------------------------------------------------
 # image branch helpers (library convolutions)
 # --------------------------------------------------------------------------------------------------
+def _to_channels_last(x):
+    """NCHW -> channels_last without torch's generic strided copy: the bf16 HRNet maps go through the tiled transpose
+    kernel (cp_transpose_cn_to_nc on (B, C, H*W)); the result is the same channels_last-strided NCHW tensor."""
+    cl = torch.channels_last
+    if x.is_contiguous(memory_format=cl):
+        return x
+    B, Cc, H, W = x.shape
+    if x.is_cuda and x.is_contiguous() and x.dtype == torch.bfloat16 and Cc % 64 == 0 and (H * W) % 64 == 0:
+        return ops.to_node_major(x.view(B, Cc, H * W), torch.bfloat16).view(B, H, W, Cc).permute(0, 3, 1, 2)
+    return x.contiguous(memory_format=cl)
+
+
 class _FoldedSeq:
     """bf16, channels_last, BN-folded functional copy of a conv stack (up_net block / single conv).
     Convolutions run on cuDNN (library part of the path); the bilinear x2 upsampling of the concatenated
@@ -333,14 +350,14 @@ class _FoldedSeq:
         cl = torch.channels_last
         start = 0
         if self.ops[0][0] == "up":
-            a = x.contiguous(memory_format=cl)
-            s = None if skip is None else skip.contiguous(memory_format=cl)
+            a = _to_channels_last(x)
+            s = None if skip is None else _to_channels_last(skip)
             x = ops.upsample2x_cat(a, s)
             start = 1
         else:
             if skip is not None:
                 x = torch.cat([x, skip], dim=1)
-            x = x.contiguous(memory_format=cl)
+            x = _to_channels_last(x)
         for kind, w, b, m, relu in self.ops[start:]:
             if kind == "conv":
                 x = self._conv_relu(x, w, b, m) if relu else F.conv2d(x, w, b, stride=m.stride, padding=m.padding,
@@ -354,7 +371,7 @@ class _FoldedSeq:
             elif kind == "lrelu":
                 x = F.leaky_relu(x, m.negative_slope)
             else:
-                x = ops.upsample2x_cat(x.contiguous(memory_format=cl), None)
+                x = ops.upsample2x_cat(_to_channels_last(x), None)
         return x
 
 

@@ -239,7 +239,9 @@ def run_ours(args):
     roof_k3 = None
     if k3:
         k3_ms = sum(k3) / len(k3)
-        k3_bytes = B * N * (4 * 64 + 256 + 512) * s_el           # taps + graph feature read, [P|Q] written
+        # min((H+1)^2 * 64, 4 * 64 * N) patch elements + graph feature read, [P|Q] written; the two launches
+        # timed here are refine stages 1 and 2 (H = 32, 64): per-launch average
+        k3_bytes = B * s_el * (N * (256 + 512) + (min(33 * 33 * 64, 256 * N) + min(65 * 65 * 64, 256 * N)) // 2)
         k3_flops = 2.0 * B * N * (512 * 256 + 256 * 256 + 256 * 512)
         ach3 = k3_bytes / (k3_ms * 1e-3) / 1e9
         roof_k3 = {"bound": "hbm", "kernel": "taps_chain_kernel (4-tap gather x mask | graph feature -> MLP x2 -> [P|Q] GEMM)",

@@ -90,6 +90,7 @@ struct EcParams {
   int npad;          // nout rounded up to 16
   int num_tiles;     // B * ceil(N / 128)
   int tiles_per_roi;
+  int tpr_shift;     // log2(tiles_per_roi) when it is a power of two (every shipped N), else -1
   int tma_out;       // bf16 output with nout % 32 == 0: the epilogue stores through the tensor map
   WTile wt[MAX_WTILES];  // order: slice-major, then column block
 };
@@ -184,8 +185,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ uint32_t a_offset(int buf, int row, int chunk) {
   return (uint32_t)(OFF_A + buf * A_BUF_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4));
 }
+__device__ __forceinline__ int tile_roi(const EcParams& kp, int tile) {
+  return kp.tpr_shift >= 0 ? (tile >> kp.tpr_shift) : tile / kp.tiles_per_roi;
+}
 __device__ __forceinline__ void tile_coords(const EcParams& kp, int tile, int& b, int& t, int& g) {
-  b = tile / kp.tiles_per_roi;
+  b = tile_roi(kp, tile);
   t = tile - b * kp.tiles_per_roi;
   g = kp.p.graph_sel ? __ldg(kp.p.graph_sel + b) : 0;
 }
@@ -355,11 +359,12 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     WQ_SET(ph, nph + U);
     const uint32_t dst = sm_base + OFF_RING + (nph + q) * 128u + sub * 16;
     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.z) + (size_t)WQ_GET(b_i) * p.N * row_bytes + sub * 16 + iss_c * 128;
+    const uint32_t mine = U > (uint32_t)q ? (U - (uint32_t)q + NUM_QW - 1) / NUM_QW : 0u;   // list entries q, q + 64, ... below U
 #pragma unroll
     for (int i = 0; i < UI; ++i)
-      if ((uint32_t)(i * NUM_QW + q) < U) {
+      if ((uint32_t)i < mine) {
         const uint32_t row = (i & 1) ? (rows2[i >> 1] >> 16) : (rows2[i >> 1] & 0xffffu);
-        cp_async16(dst + i * (NUM_QW * 128), src + row * row_bytes);
+        cp_async16(dst + i * (NUM_QW * 128), src + (size_t)row * row_bytes);
       }
     if (iss_c == 0) {  // the tile's pair programs ride along with its first round
       const uint32_t pd = sm_base + OFF_PROG + (iss_ti & 1) * PROG_BYTES;
@@ -379,7 +384,7 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
 
   uint32_t ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
-    const int b = tile / kp.tiles_per_roi, t = tile - b * kp.tiles_per_roi;
+    const int b = tile_roi(kp, tile), t = tile - b * kp.tiles_per_roi;
     const int n0 = t * TILE_M;
     const uint32_t row0 = (uint32_t)(b * p.N + n0);   // B * N < 2^31 (checked by the host)
     const uint32_t prog_s = sm_base + OFF_PROG + (ti & 1) * PROG_BYTES;
@@ -493,7 +498,7 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
   const int sw = (lane >> 1) & 3;   // SWIZZLE_64B: 16-byte chunk index ^= bits 1-2 of the row
   int ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
-    const int b = tile / kp.tiles_per_roi, t = tile - b * kp.tiles_per_roi;
+    const int b = tile_roi(kp, tile), t = tile - b * kp.tiles_per_roi;
     const int n0 = t * TILE_M;
     const int rows_valid = min(TILE_M, p.N - n0);
     const bool row_ok = row < rows_valid;
@@ -690,6 +695,9 @@ extern "C" int cp_edgeconv_fwd(const cp_edgeconv_params* pp, cp_stream_t s) {
   CP_REQUIRE(kp.npad <= TMEM_COLS, CP_E_UNSUPPORTED, "cp_edgeconv_fwd: nout=%d > 512", L.nout);
   kp.NB = (kp.npad + 127) / 128;
   kp.tiles_per_roi = (p.N + TILE_M - 1) / TILE_M;
+  kp.tpr_shift = -1;
+  for (int sft = 0; sft < 30; ++sft)
+    if ((1 << sft) == kp.tiles_per_roi) kp.tpr_shift = sft;
   kp.num_tiles = p.B * kp.tiles_per_roi;
   if (p.out_mode == CP_OUT_BF16)
     CP_REQUIRE((p.ld_out % 8) == 0 && p.ld_out >= kp.npad, CP_E_INVALID, "cp_edgeconv_fwd: bf16 output needs ld_out %% 8 == 0 and >= %d", kp.npad);

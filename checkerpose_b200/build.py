@@ -6,7 +6,8 @@ import os
 import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(CSRC, "libcheckerpose_b200.so")
+# CHECKERPOSE_B200_LIB selects another build of the same library (kernel A/B experiments, scripts/kbench.py)
+LIB_PATH = os.environ.get("CHECKERPOSE_B200_LIB") or os.path.join(CSRC, "libcheckerpose_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -24,18 +25,19 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into csrc/libcheckerpose_b200.so; returns its path."""
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Compile csrc/*.cu into csrc/libcheckerpose_b200.so (or ``out``, with extra -D ``defines``); returns its path."""
+    if out is None and not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    out = out or LIB_PATH
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -231,9 +231,11 @@ __device__ void mma_issuer(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t
         const uint32_t b_addr = smem_u32(sm + OFF_B + s * B_STAGE_BYTES);
         const uint32_t idesc = make_idesc_bf16_m128(kp.wt[c * kp.NB + nb].bytes >> 7);
         const uint32_t d = tmem_base + (uint32_t)(nb * 128);
+#ifndef CP_KO_MMA
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((c | k) != 0));
+#endif
         mma_commit(&bars->b_empty[s]);
       }
       mma_commit(&bars->a_empty[ab]);
@@ -270,6 +272,15 @@ __device__ __forceinline__ uint4 finish_node(uint4 m, uint4 q, float slope, bool
   }
   return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
+
+#ifdef CP_PROFILE_PHASES
+__device__ unsigned long long cp_dbg_phase[16];
+#define PH_T(v) const long long v = clock64()
+#define PH_ADD(i, a, b) ph[i] += (b) - (a)
+#else
+#define PH_T(v)
+#define PH_ADD(i, a, b)
+#endif
 
 template <int KCH>
 __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, int lane) {
@@ -362,7 +373,11 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     const uint32_t mine = U > (uint32_t)q ? (U - (uint32_t)q + NUM_QW - 1) / NUM_QW : 0u;   // list entries q, q + 64, ... below U
 #pragma unroll
     for (int i = 0; i < UI; ++i)
+#ifdef CP_KO_COPY    // timing experiment only (wrong results): no staging copies
+      if (false) {
+#else
       if ((uint32_t)i < mine) {
+#endif
         const uint32_t row = (i & 1) ? (rows2[i >> 1] >> 16) : (rows2[i >> 1] & 0xffffu);
         cp_async16(dst + i * (NUM_QW * 128), src + (size_t)row * row_bytes);
       }
@@ -382,6 +397,9 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     return true;
   };
 
+#ifdef CP_PROFILE_PHASES
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   uint32_t ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     const int b = tile_roi(kp, tile), t = tile - b * kp.tiles_per_roi;
@@ -389,12 +407,15 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     const uint32_t row0 = (uint32_t)(b * p.N + n0);   // B * N < 2^31 (checked by the host)
     const uint32_t prog_s = sm_base + OFF_PROG + (ti & 1) * PROG_BYTES;
     for (uint32_t c = 0; c < KC; ++c, ++it) {
+      PH_T(t0);
+#ifndef CP_KO_ISSUE
       // ---- copy ahead ----
       uint32_t iss = WQ_GET(iss);
       while (iss < total && iss <= it + LOOKAHEAD) {
         if (!try_issue(iss == it)) break;
         ++iss;
       }
+      PH_T(t1);
       // ---- signal "my copies have landed" one round early, so that warps may drift apart by a round ----
       {
         const uint32_t target = min(it + 2, iss);  // rounds < target
@@ -410,7 +431,10 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
           WQ_SET(arrived, target);
         }
       }
+      PH_T(t2);
       mbar_wait(&bars->stg_full[it % NBAR], (it / NBAR) & 1);
+#endif
+      PH_T(t3);
 
       // ---- this quarter-warp's pair; the overlap-sorted pair groups rotate over the warps from slice to slice so that
       //      every warp sees the same mix of cheap (large C) and expensive pairs over a tile ----
@@ -418,12 +442,20 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
       const uint32_t pe = prog_s + pair * (PW * 2);
       const uint32_t info = lds32(pe + 2 * KP * 2);
       const int na = info & 255, nb = (info >> 8) & 255;
+#ifdef CP_KO_READS   // timing experiment only (wrong results): no row reads
+      const uint32_t nc4 = 0, nr4 = 0;
+#else
       const uint32_t nc4 = info >> 18;              // chunks (of 4 rows) the pair shares        } warp-uniform
       const uint32_t nr4 = (uint32_t)KCH - nc4;     // chunks of each node's own rows            }
+#endif
       // own Q slices: issued first, their (L2) latency hides behind the row reads
       const bf16* zq = reinterpret_cast<const bf16*>(p.z) + p.Co + c * 64 + sub * 8;
+#ifdef CP_KO_Q
+      const uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+#else
       const uint4 qa = na != 255 ? ldg_nc_v4(zq + (size_t)(row0 + na) * p.ld_z) : make_uint4(0, 0, 0, 0);
       const uint4 qb = nb != 255 ? ldg_nc_v4(zq + (size_t)(row0 + nb) * p.ld_z) : make_uint4(0, 0, 0, 0);
+#endif
       if (c == 0 && tile + (int)gridDim.x < kp.num_tiles) {
         // pull the Q halves of the NEXT tile's rows into L2 (128 rows x Co bf16 = 2 Co lines of 128 B), so that the
         // loads above find them there one tile later
@@ -451,8 +483,11 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
         accb = max_quad(accb, stg, ob.x, ob.y);
       }
 
+      PH_T(t4);
       const uint32_t ab = it % A_BUFS;
       if (it >= A_BUFS) mbar_wait(&bars->a_empty[ab], ((it / A_BUFS) - 1) & 1);   // MMAs that read this buffer are done
+      PH_T(t5);
+#ifndef CP_KO_FINISH
       if (na != 255) {
         const uint4 o = finish_node(acc, qa, slope, fast_lrelu);
         sts128(sm_base + a_offset(ab, na, sub), o);
@@ -464,13 +499,21 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
         if (p.a_out) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.a_out) + (size_t)(row0 + nb) * p.ld_a_out + c * 64 + sub * 8) = o;
       }
       fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core's async proxy
+#endif
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&bars->a_full[ab]);
         mbar_arrive(&bars->stg_empty[it % NBAR]);
       }
+#ifdef CP_PROFILE_PHASES
+      { PH_T(t6); PH_ADD(0, t0, t1); PH_ADD(1, t1, t2); PH_ADD(2, t2, t3); PH_ADD(3, t3, t4); PH_ADD(4, t4, t5); PH_ADD(5, t5, t6); }
+#endif
     }
   }
+#ifdef CP_PROFILE_PHASES
+  if (lane == 0)
+    for (int i = 0; i < 6; ++i) atomicAdd(&cp_dbg_phase[i], (unsigned long long)ph[i]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -503,9 +546,17 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
     const int rows_valid = min(TILE_M, p.N - n0);
     const bool row_ok = row < rows_valid;
     const size_t grow0 = (size_t)b * p.N + n0;
+#ifdef CP_EPI_SLEEP_NS
+    mbar_wait_idle(&bars->acc_full, ti & 1, CP_EPI_SLEEP_NS);
+#else
     mbar_wait(&bars->acc_full, ti & 1);
+#endif
     tc_fence_after_sync();
+#ifdef CP_KO_EPI
+    for (int c0 = h * 32; c0 < 0; c0 += 32 * (NUM_EPI_WARPS / 4)) {
+#else
     for (int c0 = h * 32; c0 < kp.npad; c0 += 32 * (NUM_EPI_WARPS / 4)) {
+#endif
       uint32_t r[32];
       const int ncols = min(32, kp.npad - c0);   // 16 or 32 (npad is a multiple of 16)
       if (TMA_OUT || ncols == 32) {
@@ -548,10 +599,12 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
         }
         fence_proxy_async_smem();
         __syncwarp();
+#ifndef CP_KO_EPI_STORE
         if (lane == 0 && q * 32 < rows_valid) {
           tma_store_3d(out_map, tb, c0, n0 + q * 32, b);
           bulk_commit();
         }
+#endif
       } else if (row_ok) {
         if (p.out_mode == CP_OUT_BF16) {
           bf16* o = reinterpret_cast<bf16*>(p.out) + (grow0 + row) * p.ld_out + c0;
@@ -652,6 +705,16 @@ cudaError_t launch(const EcParams& kp, const CUtensorMap& map, int grid, cudaStr
 }
 
 }  // namespace
+
+#ifdef CP_PROFILE_PHASES
+// debug builds only: cycles the aggregator warps spent per phase (summed over warps and SMs); resets the counters
+extern "C" int cp_debug_read_phases(unsigned long long* out16) {
+  unsigned long long z[16] = {0};
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, cp_dbg_phase, sizeof(z)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(cp_dbg_phase, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int cp_edgeconv_ring_rows(int KP) {
   switch (KP) {

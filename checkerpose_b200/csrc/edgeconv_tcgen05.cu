@@ -47,16 +47,24 @@ constexpr int NUM_EPI_WARPS = 8;
 // slots, so the single-thread roles everything else waits on get the highest warp ids.
 constexpr int W_WARP = EPI_WARP0 + NUM_EPI_WARPS;                   // weight producer (+ TMEM alloc/dealloc)
 constexpr int MMA_WARP = W_WARP + 1;
-constexpr int NUM_WARPS = MMA_WARP + 3;         // two idle warps complete the control warpgroup
-constexpr int REGS_AGG = 88, REGS_EPI = 64, REGS_CTRL = 24;   // 16*88 + 8*64 + 4*24 = 28*72
-static_assert(NUM_WARPS % 4 == 0 && NUM_AGG_WARPS * REGS_AGG + NUM_EPI_WARPS * REGS_EPI + 4 * REGS_CTRL <= NUM_WARPS * 72, "register budget");
+constexpr int STG_WARP0 = MMA_WARP + 3;         // two idle warps complete the control warpgroup; then the stagers
+constexpr int NUM_STG_WARPS = 4;
+constexpr int STG_THREADS = NUM_STG_WARPS * 32;
+constexpr int NUM_WARPS = STG_WARP0 + NUM_STG_WARPS;
+#ifndef CP_REGS_AGG
+#define CP_REGS_AGG 80
+#define CP_REGS_EPI 56
+#define CP_REGS_STG 56
+#endif
+constexpr int REGS_AGG = CP_REGS_AGG, REGS_EPI = CP_REGS_EPI, REGS_CTRL = 24, REGS_STG = CP_REGS_STG;   // the kernel is launched at 64
+static_assert(NUM_WARPS == 32 && NUM_AGG_WARPS * REGS_AGG + NUM_EPI_WARPS * REGS_EPI + 4 * REGS_CTRL + NUM_STG_WARPS * REGS_STG <= NUM_WARPS * 64,
+              "register budget");
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int A_BUF_BYTES = TILE_M * 128;    // one K slice of the A operand: 128 rows x 64 bf16
 constexpr int A_BUFS = 3;
 constexpr int B_STAGE_BYTES = 128 * 128;
 constexpr int B_STAGES = 3;
 constexpr int NBAR = 4;                      // staging rounds that may be unreleased at any time
-constexpr int LOOKAHEAD = 2;                 // rounds copied ahead of the one being reduced
 constexpr int UI = CP_PLAN_UMAX / NUM_QW;    // list entries per quarter-warp
 constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: a tile of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores
 constexpr int BIAS_BYTES = 512 * 4;
@@ -70,8 +78,8 @@ constexpr int OFF_B = OFF_A + A_BUFS * A_BUF_BYTES;
 constexpr int OFF_TBUF = OFF_B + B_STAGES * B_STAGE_BYTES;
 constexpr int OFF_BIAS = OFF_TBUF + NUM_EPI_WARPS * TBUF_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
-constexpr int OFF_WQ = OFF_BAR + 256;                          // per-warp ring bookkeeping
-constexpr int OFF_PROG = OFF_WQ + NUM_AGG_WARPS * 96;
+constexpr int OFF_WQ = OFF_BAR + 256;                          // per stager warp: virtual ring position of the last NBAR rounds
+constexpr int OFF_PROG = OFF_WQ + NUM_STG_WARPS * 16 + 64;
 __host__ __device__ constexpr int prog_width(int KCH) { return 8 * KCH + 8; }      // uint16 per pair entry (= 2 KP + 8)
 __host__ __device__ constexpr int prog_bytes(int KCH) { return CP_PLAN_PAIRS * prog_width(KCH) * 2; }
 __host__ __device__ constexpr int off_ring(int KCH) { return (OFF_PROG + 2 * prog_bytes(KCH) + 127) & ~127; }
@@ -99,25 +107,11 @@ struct Bars {
   uint64_t stg_full[NBAR], stg_empty[NBAR];
   uint64_t a_full[A_BUFS], a_empty[A_BUFS];
   uint64_t b_full[B_STAGES], b_empty[B_STAGES];
-  uint64_t acc_full, acc_empty;
+  uint64_t acc_full[4], acc_empty[4];   // per 128-column block of the accumulator: the next tile's MMAs follow the epilogue block by block
   uint32_t tmem_slot;
   uint32_t bias_blocks;   // bit i: columns [32 i, 32 i + 32) have a non-zero bias (the P half of a [P|Q] layer has none)
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
-
-struct WarpQ {              // replicated per aggregator warp
-  uint32_t vstart[NBAR];    // [round % NBAR] virtual ring position (rows, monotonically increasing) of the round
-  uint32_t pstart[NBAR];    // [round % NBAR] physical start row of the round in the ring
-  uint32_t iss, iss_c, iss_ti;       // next round to copy: index, slice, tile iteration
-  uint32_t loaded_ti;                // tile iteration whose list is in the threads' rows2[]
-  uint32_t U_i, b_i, gt_i;           // of that tile: distinct rows, RoI, plan tile (g * T + t)
-  uint32_t pre_ti, pre_U;            // tile iteration (and its row count) whose list is prefetched in pre_rows
-  uint32_t vh, ph;                   // ring head: virtual and physical row
-  uint32_t rel;                      // rounds < rel are known to be released by all warps
-  uint32_t arrived;                  // rounds < arrived: this warp has signalled that its copies landed
-  uint32_t pad[3];
-};
-static_assert(sizeof(WarpQ) == 96, "OFF_PROG layout");
 
 __device__ __forceinline__ uint32_t bf2_max3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r;
@@ -194,6 +188,15 @@ __device__ __forceinline__ void tile_coords(const EcParams& kp, int tile, int& b
   g = kp.p.graph_sel ? __ldg(kp.p.graph_sel + b) : 0;
 }
 
+#ifdef CP_PROFILE_PHASES
+__device__ unsigned long long cp_dbg_phase[16];
+#define PH_T(v) const long long v = clock64()
+#define PH_ADD(i, a, b) ph[i] += (b) - (a)
+#else
+#define PH_T(v)
+#define PH_ADD(i, a, b)
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // weight producer / MMA issuer
 // ------------------------------------------------------------------------------------------------------
@@ -214,51 +217,150 @@ __device__ void weight_producer(const EcParams& kp, uint8_t* sm, Bars* bars) {
 __device__ void mma_issuer(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base) {
   uint32_t cnt = 0, it = 0;
   int ti = 0;
+#ifdef CP_PROFILE_PHASES
+  long long ph[12] = {0};
+#endif
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
-    if (ti > 0) {
-      mbar_wait(&bars->acc_empty, (ti - 1) & 1);  // epilogue of the previous tile has drained TMEM
-      tc_fence_after_sync();
-    }
     for (int c = 0; c < kp.KC; ++c, ++it) {
       const uint32_t ab = it % A_BUFS;
+      PH_T(m2);
       mbar_wait(&bars->a_full[ab], (it / A_BUFS) & 1);
+      PH_T(m3);
+      PH_ADD(9, m2, m3);
       tc_fence_after_sync();
       const uint32_t a_addr = smem_u32(sm + OFF_A + ab * A_BUF_BYTES);
       for (int nb = 0; nb < kp.NB; ++nb, ++cnt) {
         const int s = cnt % B_STAGES;
+        PH_T(m4);
         mbar_wait(&bars->b_full[s], (cnt / B_STAGES) & 1);
+        PH_T(m5);
+        PH_ADD(10, m4, m5);
         tc_fence_after_sync();
         const uint32_t b_addr = smem_u32(sm + OFF_B + s * B_STAGE_BYTES);
         const uint32_t idesc = make_idesc_bf16_m128(kp.wt[c * kp.NB + nb].bytes >> 7);
         const uint32_t d = tmem_base + (uint32_t)(nb * 128);
+        if (c == 0 && ti > 0) {
+          PH_T(m0);
+          mbar_wait(&bars->acc_empty[nb], (ti - 1) & 1);  // the epilogue of the previous tile has drained these columns
+          PH_T(m1);
+          PH_ADD(8, m0, m1);
+          tc_fence_after_sync();
+        }
 #ifndef CP_KO_MMA
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((c | k) != 0));
 #endif
         mma_commit(&bars->b_empty[s]);
+        if (c == kp.KC - 1) mma_commit(&bars->acc_full[nb]);
       }
       mma_commit(&bars->a_empty[ab]);
     }
-    mma_commit(&bars->acc_full);
+  }
+#ifdef CP_PROFILE_PHASES
+  for (int i = 8; i < 11; ++i) atomicAdd(&cp_dbg_phase[i], (unsigned long long)ph[i]);
+#endif
+}
+
+// Ring position of the next round (U rows, contiguous): a pure function of the list lengths of the tiles this CTA
+// processes, so the stagers and every aggregator warp compute it on their own and never exchange positions.
+__device__ __forceinline__ uint32_t ring_place(uint32_t& ph, uint32_t U, uint32_t R) {
+  if (ph + U > R) ph = 0;
+  const uint32_t at = ph;
+  ph += U;
+  return at;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// stagers: one warpgroup copies every round's distinct neighbour row slices into the ring
+// ------------------------------------------------------------------------------------------------------
+template <int KCH>
+__device__ void stager(const EcParams& kp, uint8_t* sm, Bars* bars, int pw, int lane) {
+  constexpr int PROG_BYTES = prog_bytes(KCH), OFF_RING = off_ring(KCH);
+  constexpr uint32_t R = ring_rows(KCH);
+  const cp_edgeconv_params& p = kp.p;
+  const cp_graph_plan& pl = p.plan;
+  const int q = pw * 4 + (lane >> 3), sub = lane & 7;   // copying quarter-warp 0..15: ring rows q, q + 16, ... of a round
+  const int tid = pw * 32 + lane;
+  const uint32_t sm_base = smem_u32(sm);
+  const uint32_t vs = sm_base + OFF_WQ + pw * 16;        // per-warp copy of vstart[NBAR] (same-value stores by all lanes)
+  const uint32_t row_bytes = (uint32_t)p.ld_z * 2;
+  const uint32_t KC = (uint32_t)kp.KC;
+  const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  uint32_t vh = 0, ph = 0;      // ring head: virtual (monotonic) and physical row
+  uint32_t rel = 0;             // rounds < rel are known to be released by all aggregator warps
+  uint32_t r = 0;               // round being copied
+  for (int ti = 0; ti < my_tiles; ++ti) {
+    int b, t, g;
+    tile_coords(kp, (int)blockIdx.x + ti * (int)gridDim.x, b, t, g);
+    const size_t gt = (size_t)g * pl.T + t;
+    const uint32_t U = (uint32_t)__ldg(pl.ucount + gt);
+    // ring row j of a round holds list entry (lane j % 64, slot j / 64): this thread copies rows j = q, q + 16, ...
+    // (the 1 KB list stays in L1 over the tile's rounds)
+    const uint16_t* lst = pl.ulist + gt * NUM_QW * UI;
+    if (ti + 1 < my_tiles) {   // next tile's list -> L2
+      int b2, t2, g2;
+      tile_coords(kp, (int)blockIdx.x + (ti + 1) * (int)gridDim.x, b2, t2, g2);
+      const size_t gt2 = (size_t)g2 * pl.T + t2;
+      if (tid < 8) prefetch_l2(pl.ulist + gt2 * NUM_QW * UI + tid * 64);
+      if (tid == 8) prefetch_l2(pl.ucount + gt2);
+    }
+    {  // the tile's own Q halves -> L2 (128 rows x Co bf16 = 2 Co lines of 128 B); the aggregators read them 2-3 rounds later
+      const uint8_t* qn = reinterpret_cast<const uint8_t*>(p.z) + ((size_t)b * p.N + (size_t)t * TILE_M) * row_bytes + p.Co * 2;
+      const int lines_per_row = p.Co >> 6;
+      const int rows_t = min(TILE_M, p.N - t * TILE_M);
+      for (int l = tid; l < rows_t * lines_per_row; l += STG_THREADS)
+        prefetch_l2(qn + (size_t)(l / lines_per_row) * row_bytes + (l % lines_per_row) * 128);
+    }
+    const uint8_t* zb = reinterpret_cast<const uint8_t*>(p.z) + (size_t)b * p.N * row_bytes + sub * 16;
+    for (uint32_t c = 0; c < KC; ++c, ++r) {
+      uint32_t nvh = vh, nph = ph;
+      if (nph + U > R) {   // a round is contiguous in the ring: skip the tail
+        nvh += R - nph;
+        nph = 0;
+      }
+      // rounds that must have been released by ALL aggregator warps before this one is copied: whatever still occupies
+      // the ring rows, the round whose barrier pair is reused, and (first round of a tile) the last round of the tile
+      // whose program buffer is overwritten
+      int need_rel = (int)r - NBAR;
+      if (c == 0) need_rel = max(need_rel, (int)r - (int)KC - 1);
+      while (rel < r) {
+        const uint32_t oldest_v = lds32(vs + (rel % NBAR) * 4);
+        if (nvh + U - oldest_v <= R && (int)rel > need_rel) break;
+        mbar_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1);
+        ++rel;
+      }
+      sts32(vs + (r % NBAR) * 4, nvh);
+      vh = nvh + U;
+      ph = nph + U;
+      const uint32_t dst = sm_base + OFF_RING + (nph + q) * 128u + sub * 16;
+      const uint8_t* src = zb + c * 128;
+#pragma unroll 4
+      for (uint32_t j = (uint32_t)q; j < U; j += 16) {
+        const uint32_t row = __ldg(lst + (j & (NUM_QW - 1)) * UI + (j >> 6));
+#ifndef CP_KO_COPY   // timing experiment only (wrong results)
+        cp_async16(dst + (j - (uint32_t)q) * 128u, src + (size_t)row * row_bytes);
+#endif
+      }
+      if (c == 0) {  // the tile's pair programs ride along with its first round
+        const uint32_t pd = sm_base + OFF_PROG + (ti & 1) * PROG_BYTES;
+        const uint8_t* prog_src = reinterpret_cast<const uint8_t*>(pl.prog) + gt * PROG_BYTES;
+        for (int piece = tid; piece < PROG_BYTES / 16; piece += STG_THREADS) cp_async16(pd + piece * 16, prog_src + piece * 16);
+      }
+      // asynchronous arrival: fires when all of this thread's copies so far have landed; nobody waits here
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->stg_full[r % NBAR])) : "memory");
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// aggregators (and staging producers)
+// aggregators
 // ------------------------------------------------------------------------------------------------------
 // max over the four staged row slices whose byte offsets are packed in w0, w1 (two uint16 each)
 __device__ __forceinline__ uint4 max_quad(uint4 m, uint32_t stg, uint32_t w0, uint32_t w1) {
   const uint4 v0 = lds128(stg + (w0 & 0xffffu)), v1 = lds128(stg + (w0 >> 16));
   const uint4 v2 = lds128(stg + (w1 & 0xffffu)), v3 = lds128(stg + (w1 >> 16));
   return bf8_max3(bf8_max3(m, v0, v1), v2, v3);
-}
-
-__device__ __forceinline__ void load_quad(uint4 (&v)[4], uint32_t stg, uint32_t w0, uint32_t w1) {
-  v[0] = lds128(stg + (w0 & 0xffffu));
-  v[1] = lds128(stg + (w0 >> 16));
-  v[2] = lds128(stg + (w1 & 0xffffu));
-  v[3] = lds128(stg + (w1 >> 16));
 }
 
 __device__ __forceinline__ uint4 finish_node(uint4 m, uint4 q, float slope, bool fast_lrelu) {
@@ -273,15 +375,6 @@ __device__ __forceinline__ uint4 finish_node(uint4 m, uint4 q, float slope, bool
   return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
-#ifdef CP_PROFILE_PHASES
-__device__ unsigned long long cp_dbg_phase[16];
-#define PH_T(v) const long long v = clock64()
-#define PH_ADD(i, a, b) ph[i] += (b) - (a)
-#else
-#define PH_T(v)
-#define PH_ADD(i, a, b)
-#endif
-
 template <int KCH>
 __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, int lane) {
   constexpr int KP = 4 * KCH, PW = prog_width(KCH), PROG_BYTES = prog_bytes(KCH), OFF_RING = off_ring(KCH);
@@ -290,150 +383,33 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
   const cp_edgeconv_params& p = kp.p;
   const cp_graph_plan& pl = p.plan;
   const int grp = lane >> 3, sub = lane & 7;
-  const int q = aw * 4 + grp;   // quarter-warp id, 0..63: copies list entries q, q+64, ...
-  const int tid = aw * 32 + lane;
   const uint32_t sm_base = smem_u32(sm);
-  const uint32_t wq = sm_base + OFF_WQ + aw * (uint32_t)sizeof(WarpQ);
   const float slope = p.agg_slope;
   const bool fast_lrelu = slope >= 0.f && slope <= 1.f;   // then lrelu(x) == max(x, slope * x)
-  const uint32_t row_bytes = (uint32_t)p.ld_z * 2;
   const uint32_t KC = (uint32_t)kp.KC;
-  const int my_tiles = (kp.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const uint32_t total = (uint32_t)my_tiles * KC;
-
-  // ---- issue side.  Its warp-uniform bookkeeping lives in shared memory (WarpQ), not in registers: every lane
-  //      executes the same updates (same-value stores), so no intra-warp synchronisation is needed ----
-#define WQ_GET(f) lds32(wq + (uint32_t)offsetof(WarpQ, f))
-#define WQ_SET(f, v) sts32(wq + (uint32_t)offsetof(WarpQ, f), (v))
-  WQ_SET(iss, 0u); WQ_SET(iss_c, 0u); WQ_SET(iss_ti, 0u); WQ_SET(loaded_ti, 0xffffffffu); WQ_SET(U_i, 0u);
-  WQ_SET(b_i, 0u); WQ_SET(gt_i, 0u); WQ_SET(pre_ti, 0xffffffffu); WQ_SET(pre_U, 0u);
-  WQ_SET(vh, 0u); WQ_SET(ph, 0u); WQ_SET(rel, 0u); WQ_SET(arrived, 0u);
-  uint32_t rows2[UI / 2] = {0, 0, 0, 0};    // this quarter-warp's rows of the tile's list, two uint16 per word
-  // the list of the tile after that one, prefetched (its load latency would otherwise stall the warp at every tile)
-  uint4 pre_rows = make_uint4(0, 0, 0, 0);
-  uint32_t it = 0;                          // round being reduced
-
-  auto prefetch_list = [&](uint32_t tix) {  // start loading the list of tile iteration tix
-    int b, t, g;
-    tile_coords(kp, (int)blockIdx.x + (int)tix * (int)gridDim.x, b, t, g);
-    const size_t gt = (size_t)g * pl.T + t;
-    WQ_SET(pre_U, (uint32_t)__ldg(pl.ucount + gt));
-    pre_rows = __ldg(reinterpret_cast<const uint4*>(pl.ulist + (gt * NUM_QW + q) * UI));
-    WQ_SET(pre_ti, tix);
-  };
-
-  // copy round `iss` into the ring if there is room; false = not now.  Unless `must` (the round is the one this warp
-  // is about to reduce), it does not wait for slower warps to release ring space -- it tries again a round later.
-  auto try_issue = [&](bool must) -> bool {
-    const uint32_t iss = WQ_GET(iss), iss_c = WQ_GET(iss_c), iss_ti = WQ_GET(iss_ti);
-    if (iss_c == 0 && WQ_GET(loaded_ti) != iss_ti) {  // the copies enter a new tile
-      if (WQ_GET(pre_ti) != iss_ti) prefetch_list(iss_ti);
-      WQ_SET(U_i, WQ_GET(pre_U));
-      rows2[0] = pre_rows.x; rows2[1] = pre_rows.y; rows2[2] = pre_rows.z; rows2[3] = pre_rows.w;
-      int b, t, g;
-      tile_coords(kp, (int)blockIdx.x + (int)iss_ti * (int)gridDim.x, b, t, g);
-      WQ_SET(b_i, (uint32_t)b);
-      WQ_SET(gt_i, (uint32_t)(g * pl.T + t));
-      WQ_SET(loaded_ti, iss_ti);
-      if ((int)iss_ti + 1 < my_tiles) prefetch_list(iss_ti + 1);
-    }
-    const uint32_t U = WQ_GET(U_i);
-    uint32_t nvh = WQ_GET(vh), nph = WQ_GET(ph);
-    if (nph + U > R) {  // a round is contiguous in the ring: skip the tail
-      nvh += R - nph;
-      nph = 0;
-    }
-    // rounds that must have been released by ALL warps: the barrier pair being reused, and (first round of a tile)
-    // the tile whose program buffer is overwritten
-    int need_rel = (int)iss - NBAR;
-    if (iss_c == 0) need_rel = max(need_rel, (int)iss - 2 * (int)KC);
-    uint32_t rel = WQ_GET(rel);
-    while (rel < iss) {
-      const uint32_t oldest_v = lds32(wq + (rel % NBAR) * 4);
-      if (nvh + U - oldest_v <= R && (int)rel > need_rel) break;
-      if (rel >= it) {  // we still hold that round ourselves: try again after reducing it
-        WQ_SET(rel, rel);
-        return false;
-      }
-      if (must) {
-        mbar_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1);
-      } else if (!mbar_try_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1)) {
-        WQ_SET(rel, rel);
-        return false;
-      }
-      ++rel;
-    }
-    WQ_SET(rel, rel);
-    sts32(wq + (iss % NBAR) * 4, nvh);
-    sts32(wq + 16 + (iss % NBAR) * 4, nph);
-    WQ_SET(vh, nvh + U);
-    WQ_SET(ph, nph + U);
-    const uint32_t dst = sm_base + OFF_RING + (nph + q) * 128u + sub * 16;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.z) + (size_t)WQ_GET(b_i) * p.N * row_bytes + sub * 16 + iss_c * 128;
-    const uint32_t mine = U > (uint32_t)q ? (U - (uint32_t)q + NUM_QW - 1) / NUM_QW : 0u;   // list entries q, q + 64, ... below U
-#pragma unroll
-    for (int i = 0; i < UI; ++i)
-#ifdef CP_KO_COPY    // timing experiment only (wrong results): no staging copies
-      if (false) {
-#else
-      if ((uint32_t)i < mine) {
-#endif
-        const uint32_t row = (i & 1) ? (rows2[i >> 1] >> 16) : (rows2[i >> 1] & 0xffffu);
-        cp_async16(dst + i * (NUM_QW * 128), src + (size_t)row * row_bytes);
-      }
-    if (iss_c == 0) {  // the tile's pair programs ride along with its first round
-      const uint32_t pd = sm_base + OFF_PROG + (iss_ti & 1) * PROG_BYTES;
-      const uint8_t* prog_src = reinterpret_cast<const uint8_t*>(pl.prog) + (size_t)WQ_GET(gt_i) * PROG_BYTES;
-      for (int piece = tid; piece < PROG_BYTES / 16; piece += AGG_THREADS) cp_async16(pd + piece * 16, prog_src + piece * 16);
-    }
-    cp_async_commit();
-    WQ_SET(iss, iss + 1);
-    if (iss_c + 1 == KC) {
-      WQ_SET(iss_c, 0u);
-      WQ_SET(iss_ti, iss_ti + 1);
-    } else {
-      WQ_SET(iss_c, iss_c + 1);
-    }
-    return true;
-  };
-
+  uint32_t it = 0;      // round being reduced
+  uint32_t ph = 0;      // ring head (replica of the stagers')
 #ifdef CP_PROFILE_PHASES
-  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long ph_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
+  auto tile_U = [&](int tile) -> uint32_t {
+    int b, t, g;
+    tile_coords(kp, tile, b, t, g);
+    return (uint32_t)__ldg(pl.ucount + (size_t)g * pl.T + t);
+  };
+  uint32_t U_next = (int)blockIdx.x < kp.num_tiles ? tile_U(blockIdx.x) : 0u;
   uint32_t ti = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     const int b = tile_roi(kp, tile), t = tile - b * kp.tiles_per_roi;
     const int n0 = t * TILE_M;
     const uint32_t row0 = (uint32_t)(b * p.N + n0);   // B * N < 2^31 (checked by the host)
     const uint32_t prog_s = sm_base + OFF_PROG + (ti & 1) * PROG_BYTES;
+    const uint32_t U = U_next;
+    if (tile + (int)gridDim.x < kp.num_tiles) U_next = tile_U(tile + (int)gridDim.x);
     for (uint32_t c = 0; c < KC; ++c, ++it) {
       PH_T(t0);
-#ifndef CP_KO_ISSUE
-      // ---- copy ahead ----
-      uint32_t iss = WQ_GET(iss);
-      while (iss < total && iss <= it + LOOKAHEAD) {
-        if (!try_issue(iss == it)) break;
-        ++iss;
-      }
-      PH_T(t1);
-      // ---- signal "my copies have landed" one round early, so that warps may drift apart by a round ----
-      {
-        const uint32_t target = min(it + 2, iss);  // rounds < target
-        const uint32_t arrived = WQ_GET(arrived);
-        if (arrived < target) {
-          const uint32_t pend = iss - target;      // younger groups that may still be in flight
-          if (pend == 0) cp_async_wait<0>();
-          else if (pend == 1) cp_async_wait<1>();
-          else cp_async_wait<2>();
-          __syncwarp();
-          if (lane == 0)
-            for (uint32_t r = arrived; r < target; ++r) mbar_arrive(&bars->stg_full[r % NBAR]);
-          WQ_SET(arrived, target);
-        }
-      }
-      PH_T(t2);
+      const uint32_t stg = sm_base + OFF_RING + ring_place(ph, U, R) * 128u + sub * 16;
       mbar_wait(&bars->stg_full[it % NBAR], (it / NBAR) & 1);
-#endif
       PH_T(t3);
 
       // ---- this quarter-warp's pair; the overlap-sorted pair groups rotate over the warps from slice to slice so that
@@ -456,18 +432,6 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
       const uint4 qa = na != 255 ? ldg_nc_v4(zq + (size_t)(row0 + na) * p.ld_z) : make_uint4(0, 0, 0, 0);
       const uint4 qb = nb != 255 ? ldg_nc_v4(zq + (size_t)(row0 + nb) * p.ld_z) : make_uint4(0, 0, 0, 0);
 #endif
-      if (c == 0 && tile + (int)gridDim.x < kp.num_tiles) {
-        // pull the Q halves of the NEXT tile's rows into L2 (128 rows x Co bf16 = 2 Co lines of 128 B), so that the
-        // loads above find them there one tile later
-        int nb_, nt_, ng_;
-        tile_coords(kp, tile + (int)gridDim.x, nb_, nt_, ng_);
-        const uint8_t* qn = reinterpret_cast<const uint8_t*>(p.z) + ((size_t)nb_ * p.N + (size_t)nt_ * TILE_M) * row_bytes + p.Co * 2;
-        const int lines_per_row = p.Co >> 6;
-        const int rows_next = min(TILE_M, p.N - nt_ * TILE_M);
-        for (int l = tid; l < rows_next * lines_per_row; l += AGG_THREADS)
-          prefetch_l2(qn + (size_t)(l / lines_per_row) * row_bytes + (l % lines_per_row) * 128);
-      }
-      const uint32_t stg = sm_base + OFF_RING + lds32(wq + 16 + (it % NBAR) * 4) * 128u + sub * 16;
 
       uint4 acc = make_uint4(NEG_INF2, NEG_INF2, NEG_INF2, NEG_INF2);
       uint32_t pa = pe;
@@ -506,13 +470,13 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
         mbar_arrive(&bars->stg_empty[it % NBAR]);
       }
 #ifdef CP_PROFILE_PHASES
-      { PH_T(t6); PH_ADD(0, t0, t1); PH_ADD(1, t1, t2); PH_ADD(2, t2, t3); PH_ADD(3, t3, t4); PH_ADD(4, t4, t5); PH_ADD(5, t5, t6); }
+      { PH_T(t6); ph_[2] += t3 - t0; ph_[3] += t4 - t3; ph_[4] += t5 - t4; ph_[5] += t6 - t5; }
 #endif
     }
   }
 #ifdef CP_PROFILE_PHASES
   if (lane == 0)
-    for (int i = 0; i < 6; ++i) atomicAdd(&cp_dbg_phase[i], (unsigned long long)ph[i]);
+    for (int i = 0; i < 6; ++i) atomicAdd(&cp_dbg_phase[i], (unsigned long long)ph_[i]);
 #endif
 }
 
@@ -540,23 +504,31 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
   const uint32_t bias_blocks = bars->bias_blocks;
   const int sw = (lane >> 1) & 3;   // SWIZZLE_64B: 16-byte chunk index ^= bits 1-2 of the row
   int ti = 0;
+#ifdef CP_PROFILE_PHASES
+  long long ph[8] = {0};
+#endif
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
     const int b = tile_roi(kp, tile), t = tile - b * kp.tiles_per_roi;
     const int n0 = t * TILE_M;
     const int rows_valid = min(TILE_M, p.N - n0);
     const bool row_ok = row < rows_valid;
     const size_t grow0 = (size_t)b * p.N + n0;
-#ifdef CP_EPI_SLEEP_NS
-    mbar_wait_idle(&bars->acc_full, ti & 1, CP_EPI_SLEEP_NS);
-#else
-    mbar_wait(&bars->acc_full, ti & 1);
-#endif
-    tc_fence_after_sync();
-#ifdef CP_KO_EPI
-    for (int c0 = h * 32; c0 < 0; c0 += 32 * (NUM_EPI_WARPS / 4)) {
-#else
-    for (int c0 = h * 32; c0 < kp.npad; c0 += 32 * (NUM_EPI_WARPS / 4)) {
-#endif
+    PH_T(e0);
+    PH_T(e1);
+    for (int c0 = h * 32; c0 < kp.NB * 128; c0 += 32 * (NUM_EPI_WARPS / 4)) {
+      if ((c0 & 127) == h * 32) {   // this warp's first block of a 128-column accumulator block
+        mbar_wait(&bars->acc_full[c0 >> 7], ti & 1);
+        tc_fence_after_sync();
+      }
+      const bool last_of_block = (c0 & 127) == h * 32 + 128 - 32 * (NUM_EPI_WARPS / 4);
+      if (c0 >= kp.npad) {          // nothing to drain in a ragged block's tail; still release the block
+        if (last_of_block) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->acc_empty[c0 >> 7]);
+        }
+        continue;
+      }
       uint32_t r[32];
       const int ncols = min(32, kp.npad - c0);   // 16 or 32 (npad is a multiple of 16)
       if (TMA_OUT || ncols == 32) {
@@ -620,11 +592,20 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
             if (c0 + e < p.n_valid) o[c0 + e] = v[e];
         }
       }
+      if (last_of_block) {   // this warp is done with the 128-column block: the next tile's MMAs may overwrite it
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[c0 >> 7]);
+      }
     }
-    tc_fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars->acc_empty);
+#ifdef CP_PROFILE_PHASES
+    { PH_T(e2); PH_ADD(6, e0, e1); PH_ADD(7, e1, e2); }
+#endif
   }
+#ifdef CP_PROFILE_PHASES
+  if (lane == 0)
+    for (int i = 6; i < 8; ++i) atomicAdd(&cp_dbg_phase[i], (unsigned long long)ph[i]);
+#endif
   if (TMA_OUT && lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last stores' reads
 }
 
@@ -637,7 +618,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NBAR; ++s) {
-      mbar_init(&bars->stg_full[s], NUM_AGG_WARPS);   // every aggregator warp once its own copies of the round landed
+      mbar_init(&bars->stg_full[s], STG_THREADS);     // every stager thread, asynchronously, once its copies of the round landed
       mbar_init(&bars->stg_empty[s], NUM_AGG_WARPS);
     }
     for (int c = 0; c < A_BUFS; ++c) {
@@ -648,8 +629,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
       mbar_init(&bars->b_full[s], 1);
       mbar_init(&bars->b_empty[s], 1);
     }
-    mbar_init(&bars->acc_full, 1);
-    mbar_init(&bars->acc_empty, NUM_EPI_WARPS);
+    for (int nb = 0; nb < 4; ++nb) {
+      mbar_init(&bars->acc_full[nb], 1);
+      mbar_init(&bars->acc_empty[nb], NUM_EPI_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == W_WARP) tmem_alloc(&bars->tmem_slot, TMEM_COLS);
@@ -667,7 +650,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_slot;
 
-  if (warp >= W_WARP) {   // control warpgroup
+  if (warp >= STG_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_STG));
+    stager<KCH>(kp, sm, bars, warp - STG_WARP0, lane);
+  } else if (warp >= W_WARP) {   // control warpgroup
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
     if (warp == MMA_WARP) {
       if (lane == 0) mma_issuer(kp, sm, bars, tmem_base);
@@ -676,7 +662,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+    if (REGS_EPI < 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const int q = warp - EPI_WARP0;
     const bool tma_out = kp.tma_out != 0;
     if (kp.p.layer.act) {

@@ -27,45 +27,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// try_wait with an explicit suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the
-// hint expires.  Measured on B200 (profiles/r01_d_edgeconv_hot_instructions.txt): without a hint a failed try_wait
-// returns after ~30 clk, and the epilogue warps' spin loops took more than half of the SM's issued instructions.
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ uint64_t global_timer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-#ifndef CP_MBAR_HINT_NS
-#define CP_MBAR_HINT_NS 20000u
-#endif
-// Bounded wait: a broken pipeline traps (-> cudaErrorLaunchFailure) after ~4 s instead of hanging the GPU box.
+// Bounded wait: a broken pipeline traps (-> cudaErrorLaunchFailure) instead of hanging the GPU box.
+// (Measured on B200: a failed try_wait returns after ~30 clk whatever suspend-time hint it is given, and neither a
+// hint nor a nanosleep back-off in the idle roles changed any kernel's time; reading %globaltimer in this loop did
+// add latency to every hand-off.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
-  while (!(CP_MBAR_HINT_NS ? mbar_try_wait_hint(bar, parity, CP_MBAR_HINT_NS) : mbar_try_wait(bar, parity))) {
-    if (global_timer_ns() - t0 > 4000000000ull) __trap();
-  }
-}
-
-// Wait of a role that idles for a long time (the epilogue between tiles): back off with nanosleep so that the spin
-// does not take issue slots from the working warps.
-__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (sleep_ns) __nanosleep(sleep_ns);
-    if (global_timer_ns() - t0 > 4000000000ull) __trap();
+    if (++spins > (1u << 27)) __trap();   // seconds
   }
 }
 

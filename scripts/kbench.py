@@ -55,9 +55,12 @@ def main():
             lib.cp_debug_read_phases(buf)
             ops.edgeconv_fwd(z=z, plan=plan, graph_sel=None, agg_slope=0.2, layer=layer, out=out, out_mode=ops.OUT_BF16)
             lib.cp_debug_read_phases(buf)
-            rounds = B * (N // 128) * 4 * 16
-            names = ["copy-ahead", "arrive(cp.async wait)", "stg_full wait", "Q+reduce", "a_empty wait", "finish+store+arrive"]
-            print("   aggregator phases, clk per warp-round: " + ", ".join(f"{n} {buf[i] / rounds:.0f}" for i, n in enumerate(names)))
+            tiles = B * (N // 128)
+            rounds = tiles * 4 * 16
+            names = ["-", "-", "stg_full wait", "Q+reduce", "a_empty wait", "finish+store+arrive"]
+            print("   aggregator, clk per warp-round: " + ", ".join(f"{n} {buf[i] / rounds:.0f}" for i, n in enumerate(names) if n != "-"))
+            print(f"   epilogue, clk per warp-tile: acc_full wait {buf[6] / tiles / 8:.0f}, drain {buf[7] / tiles / 8:.0f};  "
+                  f"MMA thread, clk per tile: acc_empty wait {buf[8] / tiles:.0f}, a_full wait {buf[9] / tiles:.0f}, b_full wait {buf[10] / tiles:.0f}")
         wq = torch.randn(C, C, generator=g) / C ** 0.5
         layer_q = ops.chain_layer(ops.pack_weight(wq.to(dev)), torch.randn(C, generator=g).to(dev), C, C, True, 0.01)
         a_out = torch.empty((B, N, C), dtype=torch.bfloat16, device=dev)

@@ -61,9 +61,15 @@ static_assert(NUM_WARPS == 32 && NUM_AGG_WARPS * REGS_AGG + NUM_EPI_WARPS * REGS
               "register budget");
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int A_BUF_BYTES = TILE_M * 128;    // one K slice of the A operand: 128 rows x 64 bf16
-constexpr int A_BUFS = 3;
+#ifndef CP_A_BUFS
+#define CP_A_BUFS 3
+#endif
+#ifndef CP_B_STAGES
+#define CP_B_STAGES 3
+#endif
+constexpr int A_BUFS = CP_A_BUFS;
 constexpr int B_STAGE_BYTES = 128 * 128;
-constexpr int B_STAGES = 3;
+constexpr int B_STAGES = CP_B_STAGES;
 constexpr int NBAR = 4;                      // staging rounds that may be unreleased at any time
 constexpr int UI = CP_PLAN_UMAX / NUM_QW;    // list entries per quarter-warp
 constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: a tile of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores

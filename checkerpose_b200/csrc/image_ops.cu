@@ -49,6 +49,10 @@ template <> struct Vec<bf16> {
   }
 };
 
+// Work decomposition: a block of 256 threads produces an 8 x 8 output-pixel patch of one slab of 8 channel vectors
+// (64 bf16 / 32 f32 channels) in two passes of 32 pixels.  The patch reads a ~5 x 5 source neighbourhood: every source
+// vector is fetched from L2 once and re-read from L1 by the ~4 outputs that use it (a pixel-linear thread order re-reads
+// all four taps of every output from L2: 4x the output bytes).
 template <typename T>
 __global__ void __launch_bounds__(256)
 upsample2x_cat_nhwc_kernel(Src a, Src b, T* __restrict__ out, int B, int H, int W, float scale_h, float scale_w) {
@@ -56,31 +60,42 @@ upsample2x_cat_nhwc_kernel(Src a, Src b, T* __restrict__ out, int B, int H, int 
   const int Ct = a.C + b.C;
   const int cv_per_px = Ct / V;
   const int OH = 2 * H, OW = 2 * W;
-  const int64_t total = (int64_t)B * OH * OW * cv_per_px;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(e % cv_per_px);
-    int64_t r = e / cv_per_px;
-    const int ox = (int)(r % OW); r /= OW;
-    const int oy = (int)(r % OH);
-    const int bi = (int)(r / OH);
-    // same arithmetic as ATen's upsample_bilinear2d with align_corners=True (accumulation type float)
-    const float hr = scale_h * (float)oy, wr = scale_w * (float)ox;
-    const int h1 = (int)hr, w1 = (int)wr;
-    const int h1p = (h1 < H - 1) ? 1 : 0, w1p = (w1 < W - 1) ? 1 : 0;
-    const float h1l = hr - (float)h1, h0l = 1.f - h1l;
-    const float w1l = wr - (float)w1, w0l = 1.f - w1l;
+  const int slabs = (cv_per_px + 7) >> 3, tx = (OW + 7) >> 3, ty = (OH + 7) >> 3;
+  const int64_t blocks = (int64_t)B * ty * tx * slabs;
+  const int cvl = threadIdx.x & 7, pl = threadIdx.x >> 3;   // channel vector in the slab, pixel 0..31 of a pass
+  for (int64_t w = blockIdx.x; w < blocks; w += gridDim.x) {
+    const int slab = (int)(w % slabs);
+    int64_t r = w / slabs;
+    const int bx = (int)(r % tx); r /= tx;
+    const int by = (int)(r % ty);
+    const int bi = (int)(r / ty);
+    const int cv = slab * 8 + cvl;
+    if (cv >= cv_per_px) continue;
     int c = cv * V;
     const Src& s = (c < a.C) ? a : b;
     if (c >= a.C) c -= a.C;
-    const T* base = reinterpret_cast<const T*>(s.p) + (int64_t)bi * s.sb + (int64_t)h1 * s.sh + (int64_t)w1 * s.sw + c;
-    float v00[V], v01[V], v10[V], v11[V], o[V];
-    Vec<T>::load(base, v00);
-    Vec<T>::load(base + w1p * s.sw, v01);
-    Vec<T>::load(base + h1p * s.sh, v10);
-    Vec<T>::load(base + h1p * s.sh + w1p * s.sw, v11);
+    const T* sbase = reinterpret_cast<const T*>(s.p) + (int64_t)bi * s.sb + c;
 #pragma unroll
-    for (int i = 0; i < V; ++i) o[i] = h0l * (w0l * v00[i] + w1l * v01[i]) + h1l * (w0l * v10[i] + w1l * v11[i]);
-    Vec<T>::store(out + e * V, o);
+    for (int pass = 0; pass < 2; ++pass) {
+      const int p = pass * 32 + pl;
+      const int oy = by * 8 + (p >> 3), ox = bx * 8 + (p & 7);
+      if (oy >= OH || ox >= OW) continue;
+      // same arithmetic as ATen's upsample_bilinear2d with align_corners=True (accumulation type float)
+      const float hr = scale_h * (float)oy, wr = scale_w * (float)ox;
+      const int h1 = (int)hr, w1 = (int)wr;
+      const int h1p = (h1 < H - 1) ? 1 : 0, w1p = (w1 < W - 1) ? 1 : 0;
+      const float h1l = hr - (float)h1, h0l = 1.f - h1l;
+      const float w1l = wr - (float)w1, w0l = 1.f - w1l;
+      const T* base = sbase + (int64_t)h1 * s.sh + (int64_t)w1 * s.sw;
+      float v00[V], v01[V], v10[V], v11[V], o[V];
+      Vec<T>::load(base, v00);
+      Vec<T>::load(base + w1p * s.sw, v01);
+      Vec<T>::load(base + h1p * s.sh, v10);
+      Vec<T>::load(base + h1p * s.sh + w1p * s.sw, v11);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = h0l * (w0l * v00[i] + w1l * v01[i]) + h1l * (w0l * v10[i] + w1l * v11[i]);
+      Vec<T>::store(out + (((int64_t)bi * OH + oy) * OW + ox) * Ct + (int64_t)cv * V, o);
+    }
   }
 }
 
@@ -102,9 +117,9 @@ extern "C" int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh,
   // align_corners=True: scale = (in - 1) / (out - 1)
   const float sh = (2 * H > 1) ? (float)(H - 1) / (float)(2 * H - 1) : 0.f;
   const float sw = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
-  const int64_t total = (int64_t)B * 2 * H * 2 * W * ((Ca + Cb) / V);
-  int64_t g = (total + 255) / 256;
-  if (g > 148 * 32) g = 148 * 32;
+  const int cvp = (Ca + Cb) / V;
+  int64_t g = (int64_t)B * ((2 * H + 7) / 8) * ((2 * W + 7) / 8) * ((cvp + 7) / 8);
+  if (g > 148 * 64) g = 148 * 64;
   if (dtype == CP_F32)
     upsample2x_cat_nhwc_kernel<float><<<(int)g, 256, 0, (cudaStream_t)s>>>(sa, sb, (float*)out, B, H, W, sh, sw);
   else

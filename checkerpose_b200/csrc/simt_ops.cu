@@ -59,6 +59,68 @@ __global__ void __launch_bounds__(256) transpose_bf16_64_kernel(const uint16_t* 
   }
 }
 
+// (B, R, S) -> (B, S, R) like the kernel above (R == 64: one output row = one 128-byte line), fused with the two steps
+// that follow the init head's conv1x1 (init.py:113-114): + bias[s] (the conv bias: s = keypoint = conv channel) and the
+// move of row s to row row_map[g(b)][s] (keypoint order -> plan order).
+__global__ void __launch_bounds__(256) transpose_scatter_bf16_64_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int R, int S,
+                                                                        const float* __restrict__ bias, const int32_t* __restrict__ row_map,
+                                                                        const int32_t* __restrict__ graph_sel) {
+  __shared__ uint32_t tile[64][33];   // [r][pair of s]
+  const int b = blockIdx.z;
+  const int s0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const uint16_t* sb = src + (size_t)b * R * S;
+  uint16_t* db = dst + (size_t)b * R * S;
+  const int t = threadIdx.x, v = t & 7, row = t >> 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = row + 32 * h;
+    const uint4 x = *reinterpret_cast<const uint4*>(sb + (size_t)(r0 + r) * S + s0 + v * 8);
+    tile[r][v * 4 + 0] = x.x; tile[r][v * 4 + 1] = x.y; tile[r][v * 4 + 2] = x.z; tile[r][v * 4 + 3] = x.w;
+  }
+  __syncthreads();
+  const int g = (row_map && graph_sel) ? graph_sel[b] : 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int sidx = row + 32 * h;   // output row = source column
+    const int sel = (sidx & 1) ? 0x7632 : 0x5410;
+    const float bs = bias ? bias[s0 + sidx] : 0.f;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t a = tile[v * 8 + 2 * j][sidx >> 1], c = tile[v * 8 + 2 * j + 1][sidx >> 1];
+      w[j] = __byte_perm(a, c, sel);
+      if (bias) {   // bf16 + f32 bias, rounded once (the reference adds the bias in the conv's accumulation type)
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        const __nv_bfloat162 o = __floats2bfloat162_rn(f.x + bs, f.y + bs);
+        w[j] = *reinterpret_cast<const uint32_t*>(&o);
+      }
+    }
+    const int drow = row_map ? row_map[(size_t)g * S + s0 + sidx] : s0 + sidx;
+    *reinterpret_cast<uint4*>(db + (size_t)drow * R + r0 + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// x (rows, C) bf16 += bias (C) f32, in place, 128-bit accesses: the bias of a library convolution that has no fused
+// activation (torch runs it as a separate broadcast add at a fraction of the HBM rate).
+__global__ void __launch_bounds__(256) bias_add_rows_kernel(uint4* __restrict__ x, const float* __restrict__ bias, int64_t vecs, int cv, int relu) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < vecs; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cv) * 8;
+    uint4 t = x[e];
+    uint32_t w[4] = {t.x, t.y, t.z, t.w};
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      float lo = f.x + bb[2 * i], hi = f.y + bb[2 * i + 1];
+      if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+      const __nv_bfloat162 o = __floats2bfloat162_rn(lo, hi);
+      w[i] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    x[e] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 template <typename TS, typename TD>
 int launch_transpose(const void* src, void* dst, int B, int R, int S, cudaStream_t st) {
   if (sizeof(TS) == 2 && sizeof(TD) == 2 && R % 64 == 0 && S % 64 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
@@ -304,8 +366,8 @@ __global__ void decode_init_kernel(const float* __restrict__ logits, int ld, int
 
 __global__ void decode_refine_kernel(const float* __restrict__ logits, int ld, int plane, int Ltot,
                                      float* __restrict__ x_bits, float* __restrict__ y_bits, int64_t* __restrict__ x_id,
-                                     int64_t* __restrict__ y_id, int B, int N, const int32_t* __restrict__ perm,
-                                     const int32_t* __restrict__ graph_sel) {
+                                     int64_t* __restrict__ y_id, int64_t* __restrict__ x_id_kp, int64_t* __restrict__ y_id_kp,
+                                     int B, int N, const int32_t* __restrict__ perm, const int32_t* __restrict__ graph_sel) {
   const int64_t total = (int64_t)B * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(e / N), n = (int)(e - (int64_t)b * N);
@@ -313,8 +375,13 @@ __global__ void decode_refine_kernel(const float* __restrict__ logits, int ld, i
     const float xv = logits[e * ld], yv = logits[e * ld + 1];
     x_bits[((size_t)b * Ltot + plane) * N + kp] = xv;
     y_bits[((size_t)b * Ltot + plane) * N + kp] = yv;
-    x_id[e] = x_id[e] * 2 + (xv > 0.f ? 1 : 0);
-    y_id[e] = y_id[e] * 2 + (yv > 0.f ? 1 : 0);
+    const int64_t xi = x_id[e] * 2 + (xv > 0.f ? 1 : 0), yi = y_id[e] * 2 + (yv > 0.f ? 1 : 0);
+    x_id[e] = xi;
+    y_id[e] = yi;
+    if (x_id_kp) {   // last stage: the ids the caller sees, in keypoint order
+      x_id_kp[(size_t)b * N + kp] = xi;
+      y_id_kp[(size_t)b * N + kp] = yi;
+    }
   }
 }
 
@@ -437,6 +504,28 @@ int cp_transpose_cn_to_nc(const void* src, int sd, void* dst, int dd, int B, int
   return CP_OK;
 }
 
+int cp_transpose_scatter_bf16(const void* src, void* dst, int B, int R, int S, const float* bias, const int32_t* row_map,
+                              const int32_t* graph_sel, cp_stream_t s) {
+  CP_REQUIRE(src && dst && src != dst && B > 0 && R > 0 && S > 0, CP_E_INVALID, "cp_transpose_scatter_bf16: bad arguments");
+  CP_REQUIRE(R % 64 == 0 && S % 64 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, CP_E_UNSUPPORTED,
+             "cp_transpose_scatter_bf16: R=%d and S=%d must be multiples of 64, pointers 16-byte aligned", R, S);
+  dim3 grid(S / 64, R / 64, B);
+  transpose_scatter_bf16_64_kernel<<<grid, 256, 0, (cudaStream_t)s>>>((const uint16_t*)src, (uint16_t*)dst, R, S, bias, row_map, graph_sel);
+  CP_CHECK_LAUNCH("cp_transpose_scatter_bf16");
+  return CP_OK;
+}
+
+int cp_bias_add_rows_bf16(void* x, const float* bias, int64_t rows, int C, int relu, cp_stream_t s) {
+  CP_REQUIRE(x && bias && rows >= 0 && C > 0, CP_E_INVALID, "cp_bias_add_rows_bf16: bad arguments");
+  CP_REQUIRE(C % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0, CP_E_UNSUPPORTED,
+             "cp_bias_add_rows_bf16: C=%d must be a multiple of 8, pointers 16-byte aligned", C);
+  if (rows == 0) return CP_OK;
+  const int64_t vecs = rows * (C / 8);
+  bias_add_rows_kernel<<<grid_for(vecs), 256, 0, (cudaStream_t)s>>>((uint4*)x, bias, vecs, C / 8, relu);
+  CP_CHECK_LAUNCH("cp_bias_add_rows_bf16");
+  return CP_OK;
+}
+
 int cp_transpose_nc_to_cn(const void* src, int sd, void* dst, int dd, int B, int N, int C, cp_stream_t s) {
   CP_REQUIRE(src && dst && B > 0 && C > 0 && N > 0, CP_E_INVALID, "cp_transpose_nc_to_cn: bad arguments");
   CP_REQUIRE(transpose_dispatch(src, sd, dst, dd, B, N, C, (cudaStream_t)s) == 0, CP_E_INVALID,
@@ -544,11 +633,13 @@ int cp_decode_init(const float* logits, int ld, int L, int Ltot, float* roi_bit,
 }
 
 int cp_decode_refine(const float* logits, int ld, int plane, int Ltot, float* x_bits, float* y_bits, int64_t* x_id,
-                     int64_t* y_id, int B, int N, const int32_t* perm, const int32_t* graph_sel, cp_stream_t s) {
+                     int64_t* y_id, int64_t* x_id_kp, int64_t* y_id_kp, int B, int N, const int32_t* perm,
+                     const int32_t* graph_sel, cp_stream_t s) {
+  CP_REQUIRE((x_id_kp == nullptr) == (y_id_kp == nullptr), CP_E_INVALID, "cp_decode_refine: x_id_kp / y_id_kp must be given together");
   CP_REQUIRE(logits && x_bits && y_bits && x_id && y_id && B > 0 && N > 0, CP_E_INVALID, "cp_decode_refine: bad arguments");
   CP_REQUIRE(plane >= 0 && plane < Ltot && ld >= 2, CP_E_INVALID, "cp_decode_refine: bad plane=%d Ltot=%d ld=%d", plane, Ltot, ld);
   decode_refine_kernel<<<grid_for((int64_t)B * N), 256, 0, (cudaStream_t)s>>>(logits, ld, plane, Ltot, x_bits, y_bits, x_id,
-                                                                              y_id, B, N, perm, graph_sel);
+                                                                              y_id, x_id_kp, y_id_kp, B, N, perm, graph_sel);
   CP_CHECK_LAUNCH("cp_decode_refine");
   return CP_OK;
 }

@@ -229,25 +229,30 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
     B = feat_last.shape[0]
     N = init_net.npoint
     dev = feat_last.device
+    bias0 = None
     with _exact_fp32_convs(dtype == torch.float32):
         if dtype == torch.bfloat16:
             conv = _bf16_module(init_net.conv1x1)
-            x0 = conv(feat_last.to(torch.bfloat16))
+            x0, bias0 = conv(feat_last.to(torch.bfloat16), defer_last_bias=True)   # bias applied by the layout change below
         else:
             x0 = init_net.conv1x1(feat_last.float())
-    # == out.view(-1, N, 64): channel = 8x8 cell (init.py:114)
-    hw = x0.shape[2] * x0.shape[3]
-    if dtype == torch.bfloat16 and x0.is_contiguous(memory_format=torch.channels_last) and not x0.is_contiguous():
-        x = ops.to_channel_major(x0.permute(0, 2, 3, 1).reshape(B, hw, N), torch.bfloat16)   # (B,hw,N) -> (B,N,hw), tiled transpose
-    else:
-        x = x0.contiguous().view(B, N, hw)
     blocks = list(init_net.pre_query_block)
     mlp = prepared_linear(init_net.mlp, dtype)
     nbits = mlp.nout
-    ctx = None
-    if blocks:
-        ctx = graph_ctx(blocks[0]._knn, obj_ids, B, dev)
-        x = ctx.to_plan(x)
+    ctx = graph_ctx(blocks[0]._knn, obj_ids, B, dev) if blocks else None
+    # == out.view(-1, N, 64): channel = 8x8 cell (init.py:114)
+    hw = x0.shape[2] * x0.shape[3]
+    if (dtype == torch.bfloat16 and x0.is_contiguous(memory_format=torch.channels_last) and not x0.is_contiguous()
+            and hw % 64 == 0 and N % 64 == 0):
+        # (B,hw,N) -> (B,N,hw) + conv bias + keypoint -> plan order in one tiled pass
+        row_map = None if ctx is None or ctx.plan.identity else ctx.plan.perm_inv
+        x = ops.transpose_scatter(x0.permute(0, 2, 3, 1).reshape(B, hw, N), bias0, row_map, None if ctx is None else ctx.sel)
+    else:
+        if bias0 is not None:
+            x0 = x0 + bias0.to(x0.dtype).view(1, -1, 1, 1)
+        x = x0.contiguous().view(B, N, hw)
+        if ctx is not None:
+            x = ctx.to_plan(x)
     if dtype == torch.float32:
         for blk in blocks:
             x = edgeconv_node_major(blk, x, ctx, dtype)
@@ -301,6 +306,7 @@ class _FoldedSeq:
     def __init__(self, module):
         mods = list(module) if isinstance(module, nn.Sequential) else [module]
         self.ops = []
+        self.bias_f32 = {}     # op index -> f32 bias (the bf16 copy in ops is what cuDNN's fused conv+bias+ReLU takes)
         i = 0
         while i < len(mods):
             m = mods[i]
@@ -323,6 +329,7 @@ class _FoldedSeq:
                     i += 1
                 self.ops.append((kind, w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
                                  None if b is None else b.to(torch.bfloat16), m, relu))
+                self.bias_f32[len(self.ops) - 1] = None if b is None else b.contiguous()
             elif isinstance(m, nn.ReLU):
                 self.ops.append(("relu", None, None, m, False))
             elif isinstance(m, nn.LeakyReLU):
@@ -346,9 +353,23 @@ class _FoldedSeq:
                 cls._fused_relu_ok = False
         return torch.relu_(F.conv2d(x, w, b, stride=m.stride, padding=m.padding, dilation=m.dilation, groups=m.groups))
 
-    def __call__(self, x, skip=None):
+    @staticmethod
+    def _bias_act(y, bias_f32, relu):
+        """[relu](y + bias) in place on a channels-last conv output: one pass of cp_bias_add_rows_bf16 instead of torch's
+        broadcast add (+ clamp)."""
+        v = y.permute(0, 2, 3, 1)
+        if bias_f32 is not None and v.is_contiguous() and v.shape[-1] % 8 == 0:
+            ops.bias_add_rows_(v, bias_f32, relu)
+            return y
+        if bias_f32 is not None:
+            y = y + bias_f32.to(y.dtype).view(1, -1, 1, 1)
+        return torch.relu_(y) if relu else y
+
+    def __call__(self, x, skip=None, defer_last_bias=False):
+        """defer_last_bias: return (y, bias) with the last convolution's bias NOT applied (its consumer fuses it)."""
         cl = torch.channels_last
         start = 0
+        last = len(self.ops) - 1
         if self.ops[0][0] == "up":
             a = _to_channels_last(x)
             s = None if skip is None else _to_channels_last(skip)
@@ -358,21 +379,25 @@ class _FoldedSeq:
             if skip is not None:
                 x = torch.cat([x, skip], dim=1)
             x = _to_channels_last(x)
-        for kind, w, b, m, relu in self.ops[start:]:
+        for oi, (kind, w, b, m, relu) in enumerate(self.ops[start:], start):
             if kind == "conv":
-                x = self._conv_relu(x, w, b, m) if relu else F.conv2d(x, w, b, stride=m.stride, padding=m.padding,
-                                                                      dilation=m.dilation, groups=m.groups)
+                if relu and b is not None:
+                    x = self._conv_relu(x, w, b, m)
+                else:
+                    x = F.conv2d(x, w, None, stride=m.stride, padding=m.padding, dilation=m.dilation, groups=m.groups)
+                    if defer_last_bias and oi == last and not relu:
+                        return x, self.bias_f32[oi]
+                    x = self._bias_act(x, self.bias_f32[oi], relu)
             elif kind == "convT":
-                x = F.conv_transpose2d(x, w, b, stride=m.stride, padding=m.padding, output_padding=m.output_padding)
-                if relu:
-                    x = torch.relu_(x)
+                x = F.conv_transpose2d(x, w, None, stride=m.stride, padding=m.padding, output_padding=m.output_padding)
+                x = self._bias_act(x, self.bias_f32[oi], relu)
             elif kind == "relu":
                 x = torch.relu_(x)
             elif kind == "lrelu":
                 x = F.leaky_relu(x, m.negative_slope)
             else:
                 x = ops.upsample2x_cat(_to_channels_last(x), None)
-        return x
+        return (x, None) if defer_last_bias else x
 
 
 def _bf16_module(module):
@@ -518,8 +543,13 @@ def pose_head_forward(net, img_feats, obj_ids=None, stage=None, dtype=None, bbox
         img_feat = image_block(net.up_net[i], img_feat, dtype, skip=img_feats[-i - 1] if i > 0 else None)
         ctx = _stage_ctx(net, net.refine_net[i], obj_ids, B, dev, ctx0)
         logits, gfeat = refine_node_major(net.refine_net[i], img_feat, gfeat, roi_mask, x_id, y_id, ctx, dtype)
-        ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id, perm, sel)
-    if perm is not None:
+        if perm is not None and i == nact - 1:   # last stage: the ids the caller sees, in keypoint order
+            x_kp, y_kp = torch.empty_like(x_id), torch.empty_like(y_id)
+            ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id, perm, sel, x_kp, y_kp)
+            x_id, y_id = x_kp, y_kp
+        else:
+            ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id, perm, sel)
+    if perm is not None and nact == 0:
         x_id = ops.permute_rows(x_id.view(B, N, 1), perm, sel, True).view(B, N)
         y_id = ops.permute_rows(y_id.view(B, N, 1), perm, sel, True).view(B, N)
     seg = image_block(net.seg_block, img_feat, dtype).float().contiguous()

@@ -102,6 +102,28 @@ def to_channel_major(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
+def transpose_scatter(x: torch.Tensor, bias=None, row_map=None, graph_sel=None) -> torch.Tensor:
+    """contiguous bf16 (B,R,S) -> (B,S,R) with out[b, row_map[g(b)][s], r] = x[b, r, s] + bias[s] (cp_transpose_scatter_bf16)."""
+    _need_cuda(x, bias, row_map, graph_sel)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    B, R, S = x.shape
+    out = torch.empty((B, S, R), dtype=torch.bfloat16, device=x.device)
+    check(lib.cp_transpose_scatter_bf16(_p(x), _p(out), B, R, S, _p(bias), _p(row_map), _p(graph_sel), _stream()),
+          "cp_transpose_scatter_bf16")
+    _count()
+    return out
+
+
+def bias_add_rows_(x: torch.Tensor, bias: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    """x (..., C) bf16, channels contiguous: x = [relu](x + bias (C) f32) in place (cp_bias_add_rows_bf16)."""
+    _need_cuda(x, bias)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and bias.dtype == torch.float32 and bias.is_contiguous()
+    Cc = x.shape[-1]
+    check(lib.cp_bias_add_rows_bf16(_p(x), _p(bias), x.numel() // Cc, Cc, int(bool(relu)), _stream()), "cp_bias_add_rows_bf16")
+    _count()
+    return x
+
+
 def convert(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     _need_cuda(x)
     if x.dtype == dtype:
@@ -314,6 +336,7 @@ class GraphPlan:
             self.max_unique = N
             self.staged, self.identity = False, True
             self.perm = torch.arange(N, dtype=torch.int32, device=dev).expand(G, N).contiguous()
+            self.perm_inv = self.perm
             self.idx_p = idx32.contiguous()
             self.ucount = self.ulist = self.prog = self.struct = None
             return
@@ -332,6 +355,9 @@ class GraphPlan:
         self.staged = worst <= min(PLAN_UMAX, self.ring_rows)
         self.identity = bool((perm == torch.arange(N, dtype=torch.int32)).all())
         self.perm = perm.to(dev)
+        inv = torch.empty_like(perm)
+        inv.scatter_(1, perm.long(), torch.arange(N, dtype=torch.int32).expand(G, N).contiguous())
+        self.perm_inv = inv.to(dev)        # keypoint id -> plan position
         self.idx_p = idx_p.to(dev)
         self.ucount, self.ulist, self.prog = ucount.to(dev), ulist.to(dev), prog.to(dev)
         self.struct = GraphPlanStruct(G, N, K, KP, T, PLAN_UMAX, self.max_unique, self.ucount.data_ptr(), self.ulist.data_ptr(),
@@ -375,11 +401,12 @@ def decode_init(logits, L, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id, 
     _count()
 
 
-def decode_refine(logits, plane, Ltot, x_bits, y_bits, x_id, y_id, perm=None, graph_sel=None):
-    _need_cuda(logits, x_bits, y_bits, x_id, y_id, perm, graph_sel)
+def decode_refine(logits, plane, Ltot, x_bits, y_bits, x_id, y_id, perm=None, graph_sel=None, x_id_kp=None, y_id_kp=None):
+    """x_id_kp / y_id_kp (B,N) int64: also write the updated ids in keypoint order (last stage)."""
+    _need_cuda(logits, x_bits, y_bits, x_id, y_id, perm, graph_sel, x_id_kp, y_id_kp)
     B, N = x_id.shape
-    check(lib.cp_decode_refine(_p(logits), logits.shape[-1], plane, Ltot, _p(x_bits), _p(y_bits), _p(x_id), _p(y_id), B, N,
-                               _p(perm), _p(graph_sel), _stream()), "cp_decode_refine")
+    check(lib.cp_decode_refine(_p(logits), logits.shape[-1], plane, Ltot, _p(x_bits), _p(y_bits), _p(x_id), _p(y_id),
+                               _p(x_id_kp), _p(y_id_kp), B, N, _p(perm), _p(graph_sel), _stream()), "cp_decode_refine")
     _count()
 
 

@@ -54,6 +54,16 @@ int cp_knn(const float* x, int B, int C, int N, int k, int64_t* idx64, int32_t* 
 int cp_transpose_cn_to_nc(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C, int N, cp_stream_t s);
 int cp_transpose_nc_to_cn(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int N, int C, cp_stream_t s);
 int cp_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, cp_stream_t s);
+/* The layout change after the init head's conv1x1 (init.py:113-114, `out.view(-1, N, 64)` of the channels-last conv
+ * output) fused with the conv bias and the keypoint -> plan renumbering: bf16 src (B, R, S) -> dst (B, S, R) with
+ * dst[b, row_map[g(b)][s], r] = src[b, r, s] + bias[s].  bias (S) f32 or NULL; row_map (G, S) int32 or NULL (identity);
+ * graph_sel (B) int32 or NULL (graph 0).  R and S multiples of 64, out of place. */
+int cp_transpose_scatter_bf16(const void* src, void* dst, int B, int R, int S, const float* bias, const int32_t* row_map,
+                              const int32_t* graph_sel, cp_stream_t s);
+/* x (rows, C) bf16 = [relu](x + bias (C) f32) in place: the bias of a library convolution without fused activation
+ * (Index2Feat_module.patch_generator pipeline.py:144-145, seg_block :349, the folded BN shift of up_net[0]'s
+ * ConvTranspose2d :186-197) on its channels-last output.  C multiple of 8. */
+int cp_bias_add_rows_bf16(void* x, const float* bias, int64_t rows, int C, int relu, cp_stream_t s);
 
 /* ---- get_graph_feature(x, knn_idx, batch_indices)  pipeline.py:27-40 ------------------------
  * Kept for API completeness (the fused path never materialises it).
@@ -216,10 +226,11 @@ int cp_decode_init(const float* logits, int ld, int L, int Ltot, float* roi_bit,
                    float* roi_mask, int64_t* x_id, int64_t* y_id, int B, int N, const int32_t* perm,
                    const int32_t* graph_sel, cp_stream_t s);
 /* Refine stage (pipeline.py:375-381): logits (B*N, ld) rows = [x_new, y_new]; writes plane `plane` of
- * x_bits / y_bits and updates id = 2*id + bit in place. */
+ * x_bits / y_bits and updates id = 2*id + bit in place; x_id_kp / y_id_kp (B, N) int64 or both NULL: the updated ids
+ * also in keypoint order (the last stage's: what PoseNet_GNNskip.forward returns). */
 int cp_decode_refine(const float* logits, int ld, int plane, int Ltot, float* x_bits, float* y_bits,
-                     int64_t* x_id, int64_t* y_id, int B, int N, const int32_t* perm, const int32_t* graph_sel,
-                     cp_stream_t s);
+                     int64_t* x_id, int64_t* y_id, int64_t* x_id_kp, int64_t* y_id_kp, int B, int N,
+                     const int32_t* perm, const int32_t* graph_sel, cp_stream_t s);
 /* Plan order <-> keypoint order for node-major rows of row_bytes bytes (multiple of 4), out of place:
  * to_keypoint_order != 0: dst[b, perm[g(b)][n], :] = src[b, n, :];  == 0: dst[b, n, :] = src[b, perm[g(b)][n], :]. */
 int cp_permute_rows(const void* src, void* dst, int row_bytes, int B, int N, const int32_t* perm,

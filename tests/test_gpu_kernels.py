@@ -452,3 +452,34 @@ def test_permute_rows_roundtrip(cp):
         want = torch.gather(t, 1, perm[:, :, None].expand(-1, -1, t.shape[2]))
         assert torch.equal(p, want)
         assert torch.equal(cp.ops.permute_rows(p, plan.perm, sel, True), t)
+
+
+def test_transpose_scatter_bias(cp):
+    """cp_transpose_scatter_bf16 = the init head's layout change (init.py:113-114) + conv bias + keypoint -> plan order."""
+    ops = cp.ops
+    g = torch.Generator().manual_seed(11)
+    B, R, S, G = 3, 64, 320, 2
+    x = _bf16_round(torch.randn(B, R, S, generator=g))
+    bias = torch.randn(S, generator=g)
+    inv = torch.stack([torch.randperm(S, generator=g) for _ in range(G)]).int()
+    sel = torch.tensor([1, 0, 1], dtype=torch.int32)
+    ref = torch.empty(B, S, R)
+    for b in range(B):
+        ref[b, inv[sel[b]].long()] = _bf16_round(x[b].t() + bias[:, None])
+    got = ops.transpose_scatter(x.cuda().to(torch.bfloat16), bias.cuda(), inv.cuda(), sel.cuda())
+    assert torch.equal(got.cpu().float(), ref)
+    plain = ops.transpose_scatter(x.cuda().to(torch.bfloat16))
+    assert torch.equal(plain.cpu().float(), x.transpose(1, 2))
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_bias_add_rows(cp, relu):
+    ops = cp.ops
+    g = torch.Generator().manual_seed(12)
+    x = _bf16_round(torch.randn(5, 7, 9, 64, generator=g))
+    bias = torch.randn(64, generator=g)
+    ref = x + bias
+    if relu:
+        ref = ref.clamp_min(0)
+    got = ops.bias_add_rows_(x.cuda().to(torch.bfloat16), bias.cuda(), relu)
+    assert torch.equal(got.cpu().float(), _bf16_round(ref))

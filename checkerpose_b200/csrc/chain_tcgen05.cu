@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_kernel(const __grid_constan
 
   const int my_tiles = (kp.num_node_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const long long total_w = (long long)my_tiles * kp.T;
-  long long pc = 0;       // weight tiles issued (producer thread only)
+  long long pc = 0;       // weight tiles issued (producer warp only)
   long long mc = 0;       // weight tiles consumed (tracked uniformly by all threads)
   uint32_t acc_n = 0;     // accumulator-barrier phases consumed (uniform)
-  const bool is_mma = (warp == 0 && lane == 0);
-  const bool is_prod = (warp == 1 && lane == 0);
+  // warps 0 / 1 run the MMA issue / weight streaming loops warp-uniformly; an elected lane issues the single-thread
+  // instructions (under an `if (lane == 0)` region ptxas wraps every tcgen05.mma in a uniform-register broadcast loop)
 
   for (int tile = blockIdx.x; tile < kp.num_node_tiles; tile += gridDim.x) {
     const int b = tile / kp.tiles_per_roi;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_kernel(const __grid_constan
           const int ntiles = nblk * kc_count;
           const long long mc_end = mc + ntiles;
           if (warp == 0) {
-            if (is_mma) {
+            {
               tc_fence_after_sync();
               for (int nbi = 0; nbi < nblk; ++nbi) {
                 for (int kci = 0; kci < kc_count; ++kci) {
@@ -350,19 +350,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_kernel(const __grid_constan
                   const uint32_t a_addr = smem_u32(sm.A + kci * A_CHUNK_BYTES);
                   const uint32_t b_addr = smem_u32(sm.Bst + s * B_STAGE_BYTES);
                   const uint32_t d = tmem_base + (uint32_t)(nbi * 128);
+                  if (elect_one()) {
 #pragma unroll
-                  for (int k = 0; k < KCHUNK / 16; ++k) {
-                    mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
-                                (uint32_t)((kci | k | ph) != 0));
+                    for (int k = 0; k < KCHUNK / 16; ++k) {
+                      mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
+                                  (uint32_t)((kci | k | ph) != 0));
+                    }
+                    mma_commit(&sm.empty[s]);
                   }
-                  mma_commit(&sm.empty[s]);
+                  __syncwarp();
                 }
               }
-              mma_commit(sm.acc);
+              if (elect_one()) mma_commit(sm.acc);
             }
             __syncwarp();
           } else if (warp == 1) {
-            if (is_prod) {
+            {
               long long limit = mc_end + STAGES;
               if (limit > total_w) limit = total_w;
               while (pc < limit) {
@@ -370,8 +373,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_kernel(const __grid_constan
                 const long long use = pc / STAGES;
                 if (use > 0) mbar_wait(&sm.empty[s], (uint32_t)((use - 1) & 1));
                 const WTile& wt = kp.wt[(int)(pc % kp.T)];
-                mbar_arrive_expect_tx(&sm.full[s], wt.bytes);
-                bulk_g2s(sm.Bst + s * B_STAGE_BYTES, wt.ptr, wt.bytes, &sm.full[s]);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&sm.full[s], wt.bytes);
+                  bulk_g2s(sm.Bst + s * B_STAGE_BYTES, wt.ptr, wt.bytes, &sm.full[s]);
+                }
+                __syncwarp();
                 ++pc;
               }
             }

@@ -68,7 +68,11 @@ constexpr int A_BUF_BYTES = TILE_M * 128;    // one K slice of the A operand: 12
 #define CP_B_STAGES 3
 #endif
 constexpr int A_BUFS = CP_A_BUFS;
-constexpr int B_STAGE_BYTES = 128 * 128;
+#ifndef CP_MMA_N
+#define CP_MMA_N 128                         // columns per tcgen05.mma (128 or 256): 256 halves the A-operand re-reads
+#endif
+constexpr int MMA_N = CP_MMA_N;
+constexpr int B_STAGE_BYTES = MMA_N * 128;   // one K slice of MMA_N weight rows
 constexpr int B_STAGES = CP_B_STAGES;
 constexpr int NBAR = 4;                      // staging rounds that may be unreleased at any time
 constexpr int UI = CP_PLAN_UMAX / NUM_QW;    // list entries per quarter-warp
@@ -82,7 +86,11 @@ static_assert(UI == 8 && NUM_QW == CP_PLAN_LIST_LANES, "the issue path loads a q
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + A_BUFS * A_BUF_BYTES;
 constexpr int OFF_TBUF = OFF_B + B_STAGES * B_STAGE_BYTES;
-constexpr int OFF_BIAS = OFF_TBUF + NUM_EPI_WARPS * TBUF_BYTES;
+#ifndef CP_TBUFS
+#define CP_TBUFS 1                           // store tiles per epilogue warp (2: the next block is written while the TMA engine reads this one)
+#endif
+constexpr int TBUFS = CP_TBUFS;
+constexpr int OFF_BIAS = OFF_TBUF + NUM_EPI_WARPS * TBUFS * TBUF_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
 constexpr int OFF_WQ = OFF_BAR + 256;                          // per stager warp: virtual ring position of the last NBAR rounds
 constexpr int OFF_PROG = OFF_WQ + NUM_STG_WARPS * 16 + 64;
@@ -194,6 +202,13 @@ __device__ __forceinline__ void tile_coords(const EcParams& kp, int tile, int& b
   g = kp.p.graph_sel ? __ldg(kp.p.graph_sel + b) : 0;
 }
 
+#ifdef CP_TRACE
+// debug builds only: clock64 timestamps of CTA 0's hand-offs (role r writes cp_trace[r * 1024 + k])
+__device__ long long cp_trace[8 * 1024];
+#define TR(role, k) do { if (blockIdx.x == 0 && (k) < 1024 && ((role) != 0 || (threadIdx.x & 31) == 0)) cp_trace[(role) * 1024 + (k)] = clock64(); } while (0)
+#else
+#define TR(role, k)
+#endif
 #ifdef CP_PROFILE_PHASES
 __device__ unsigned long long cp_dbg_phase[16];
 #define PH_T(v) const long long v = clock64()
@@ -207,16 +222,25 @@ __device__ unsigned long long cp_dbg_phase[16];
 // weight producer / MMA issuer
 // ------------------------------------------------------------------------------------------------------
 __device__ void weight_producer(const EcParams& kp, uint8_t* sm, Bars* bars) {
-  const int T = kp.KC * kp.NB;
+  constexpr int SUB = MMA_N / 128;     // packed 128-row tiles per stage
+  const int NBM = (kp.NB + SUB - 1) / SUB;
   uint32_t cnt = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x) {
-    for (int w = 0; w < T; ++w, ++cnt) {
-      const int s = cnt % B_STAGES;
-      const uint32_t use = cnt / B_STAGES;
-      if (use > 0) mbar_wait(&bars->b_empty[s], (use - 1) & 1);
-      mbar_arrive_expect_tx(&bars->b_full[s], kp.wt[w].bytes);
-      bulk_g2s(sm + OFF_B + s * B_STAGE_BYTES, kp.wt[w].ptr, kp.wt[w].bytes, &bars->b_full[s]);
-    }
+    for (int c = 0; c < kp.KC; ++c)
+      for (int nbm = 0; nbm < NBM; ++nbm, ++cnt) {
+        const int s = cnt % B_STAGES;
+        const uint32_t use = cnt / B_STAGES;
+        if (use > 0) mbar_wait(&bars->b_empty[s], (use - 1) & 1);
+        const WTile& w0 = kp.wt[c * kp.NB + nbm * SUB];
+        const bool two = SUB == 2 && nbm * SUB + 1 < kp.NB;
+        const uint32_t bytes1 = two ? kp.wt[c * kp.NB + nbm * SUB + 1].bytes : 0u;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->b_full[s], w0.bytes + bytes1);
+          bulk_g2s(sm + OFF_B + s * B_STAGE_BYTES, w0.ptr, w0.bytes, &bars->b_full[s]);
+          if (two) bulk_g2s(sm + OFF_B + s * B_STAGE_BYTES + 128 * 128, kp.wt[c * kp.NB + nbm * SUB + 1].ptr, bytes1, &bars->b_full[s]);
+        }
+        __syncwarp();
+      }
   }
 }
 
@@ -233,9 +257,12 @@ __device__ void mma_issuer(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t
       mbar_wait(&bars->a_full[ab], (it / A_BUFS) & 1);
       PH_T(m3);
       PH_ADD(9, m2, m3);
+      TR(0, it * 4 + 0);
       tc_fence_after_sync();
       const uint32_t a_addr = smem_u32(sm + OFF_A + ab * A_BUF_BYTES);
-      for (int nb = 0; nb < kp.NB; ++nb, ++cnt) {
+      constexpr int SUB = MMA_N / 128;
+      const int NBM = (kp.NB + SUB - 1) / SUB;
+      for (int nbm = 0; nbm < NBM; ++nbm, ++cnt) {
         const int s = cnt % B_STAGES;
         PH_T(m4);
         mbar_wait(&bars->b_full[s], (cnt / B_STAGES) & 1);
@@ -243,24 +270,33 @@ __device__ void mma_issuer(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t
         PH_ADD(10, m4, m5);
         tc_fence_after_sync();
         const uint32_t b_addr = smem_u32(sm + OFF_B + s * B_STAGE_BYTES);
-        const uint32_t idesc = make_idesc_bf16_m128(kp.wt[c * kp.NB + nb].bytes >> 7);
-        const uint32_t d = tmem_base + (uint32_t)(nb * 128);
+        const int nb0 = nbm * SUB, nb1 = min(nb0 + SUB, kp.NB);     // 128-column accumulator blocks this MMA covers
+        uint32_t ncols = 0;
+        for (int nb = nb0; nb < nb1; ++nb) ncols += kp.wt[c * kp.NB + nb].bytes >> 7;
+        const uint32_t idesc = make_idesc_bf16_m128(ncols);
+        const uint32_t d = tmem_base + (uint32_t)(nb0 * 128);
         if (c == 0 && ti > 0) {
           PH_T(m0);
-          mbar_wait(&bars->acc_empty[nb], (ti - 1) & 1);  // the epilogue of the previous tile has drained these columns
+          for (int nb = nb0; nb < nb1; ++nb) mbar_wait(&bars->acc_empty[nb], (ti - 1) & 1);  // the epilogue of the previous tile has drained these columns
           PH_T(m1);
           PH_ADD(8, m0, m1);
           tc_fence_after_sync();
         }
+        if (elect_one()) {
 #ifndef CP_KO_MMA
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((c | k) != 0));
+          for (int k = 0; k < 4; ++k)
+            mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((c | k) != 0));
 #endif
-        mma_commit(&bars->b_empty[s]);
-        if (c == kp.KC - 1) mma_commit(&bars->acc_full[nb]);
+          mma_commit(&bars->b_empty[s]);
+          if (c == kp.KC - 1)
+            for (int nb = nb0; nb < nb1; ++nb) mma_commit(&bars->acc_full[nb]);
+        }
+        __syncwarp();
       }
-      mma_commit(&bars->a_empty[ab]);
+      if (elect_one()) mma_commit(&bars->a_empty[ab]);
+      __syncwarp();
+      TR(0, it * 4 + 1);
     }
   }
 #ifdef CP_PROFILE_PHASES
@@ -336,6 +372,7 @@ __device__ void stager(const EcParams& kp, uint8_t* sm, Bars* bars, int pw, int 
         mbar_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1);
         ++rel;
       }
+      if (tid == 0) TR(5, r * 2 + 0);
       sts32(vs + (r % NBAR) * 4, nvh);
       vh = nvh + U;
       ph = nph + U;
@@ -355,6 +392,7 @@ __device__ void stager(const EcParams& kp, uint8_t* sm, Bars* bars, int pw, int 
       }
       // asynchronous arrival: fires when all of this thread's copies so far have landed; nobody waits here
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->stg_full[r % NBAR])) : "memory");
+      if (tid == 0) TR(5, r * 2 + 1);
     }
   }
 }
@@ -415,7 +453,9 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
     for (uint32_t c = 0; c < KC; ++c, ++it) {
       PH_T(t0);
       const uint32_t stg = sm_base + OFF_RING + ring_place(ph, U, R) * 128u + sub * 16;
+      if (lane == 0 && (aw == 0 || aw == 15)) TR(1 + (aw == 15), it * 4 + 0);
       mbar_wait(&bars->stg_full[it % NBAR], (it / NBAR) & 1);
+      if (lane == 0 && (aw == 0 || aw == 15)) TR(1 + (aw == 15), it * 4 + 1);
       PH_T(t3);
 
       // ---- this quarter-warp's pair; the overlap-sorted pair groups rotate over the warps from slice to slice so that
@@ -455,7 +495,9 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
 
       PH_T(t4);
       const uint32_t ab = it % A_BUFS;
+      if (lane == 0 && (aw == 0 || aw == 15)) TR(1 + (aw == 15), it * 4 + 2);
       if (it >= A_BUFS) mbar_wait(&bars->a_empty[ab], ((it / A_BUFS) - 1) & 1);   // MMAs that read this buffer are done
+      if (lane == 0 && (aw == 0 || aw == 15)) TR(1 + (aw == 15), it * 4 + 3);
       PH_T(t5);
 #ifndef CP_KO_FINISH
       if (na != 255) {
@@ -504,7 +546,8 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
   const int row = q * 32 + lane;
   const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
   const uint32_t sm_base = smem_u32(sm);
-  const uint32_t tbuf = sm_base + OFF_TBUF + ew * TBUF_BYTES;
+  const uint32_t tbuf = sm_base + OFF_TBUF + ew * (TBUFS * TBUF_BYTES);
+  uint32_t nstore = 0;   // TMA stores issued by this warp
   const uint32_t bias_s = sm_base + OFF_BIAS;
   const float slope = L.slope;
   const uint32_t bias_blocks = bars->bias_blocks;
@@ -526,6 +569,7 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
         mbar_wait(&bars->acc_full[c0 >> 7], ti & 1);
         tc_fence_after_sync();
       }
+      if (lane == 0 && (ew == 0 || ew == 7)) TR(3 + (ew == 7), ti * 8 + (c0 >> 6));
       const bool last_of_block = (c0 & 127) == h * 32 + 128 - 32 * (NUM_EPI_WARPS / 4);
       if (c0 >= kp.npad) {          // nothing to drain in a ragged block's tail; still release the block
         if (last_of_block) {
@@ -566,8 +610,9 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
       if (TMA_OUT) {
         // 32 rows x 64 B tile in the SWIZZLE_64B layout of the tensor map; the TMA engine writes it to
         // out[b, n0 + 32 q .. +32, c0 .. c0+32) and clips rows beyond N
-        const uint32_t tb = tbuf;
-        if (lane == 0) bulk_wait_read<0>();   // the previous store is done reading the buffer
+        const uint32_t tb = tbuf + (nstore % TBUFS) * TBUF_BYTES;
+        ++nstore;
+        if (lane == 0) bulk_wait_read<TBUFS - 1>();   // the store that last used this buffer is done reading it
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -662,9 +707,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
   } else if (warp >= W_WARP) {   // control warpgroup
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
     if (warp == MMA_WARP) {
-      if (lane == 0) mma_issuer(kp, sm, bars, tmem_base);
+      mma_issuer(kp, sm, bars, tmem_base);
     } else if (warp == W_WARP) {
-      if (lane == 0) weight_producer(kp, sm, bars);
+      weight_producer(kp, sm, bars);
     }
     __syncwarp();
   } else if (warp >= EPI_WARP0) {
@@ -698,6 +743,12 @@ cudaError_t launch(const EcParams& kp, const CUtensorMap& map, int grid, cudaStr
 
 }  // namespace
 
+#ifdef CP_TRACE
+extern "C" int cp_debug_read_trace(long long* out, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, cp_trace, sizeof(long long) * (size_t)(n < 8 * 1024 ? n : 8 * 1024)) == cudaSuccess ? 0 : -1;
+}
+#endif
 #ifdef CP_PROFILE_PHASES
 // debug builds only: cycles the aggregator warps spent per phase (summed over warps and SMs); resets the counters
 extern "C" int cp_debug_read_phases(unsigned long long* out16) {

@@ -39,6 +39,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp (elect.sync): the single-thread instructions (tcgen05.mma / commit, bulk copies) are
+// issued under this predicate while the surrounding control flow stays warp-uniform, so that ptxas keeps their
+// operands in uniform registers (under an `if (lane == 0)` region it wraps every one of them in a broadcast loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------------
 // Make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

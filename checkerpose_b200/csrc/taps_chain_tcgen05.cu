@@ -174,8 +174,11 @@ __device__ void weight_producer(const TcParams& kp, uint8_t* sm, Bars* bars) {
       const int s = cnt % B_STAGES;
       const uint32_t use = cnt / B_STAGES;
       if (use > 0) mbar_wait(&bars->b_empty[s], (use - 1) & 1);
-      mbar_arrive_expect_tx(&bars->b_full[s], kp.wt[w].bytes);
-      bulk_g2s(sm + OFF_B + s * B_STAGE_BYTES, kp.wt[w].ptr, kp.wt[w].bytes, &bars->b_full[s]);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bars->b_full[s], kp.wt[w].bytes);
+        bulk_g2s(sm + OFF_B + s * B_STAGE_BYTES, kp.wt[w].ptr, kp.wt[w].bytes, &bars->b_full[s]);
+      }
+      __syncwarp();
     }
   }
 }
@@ -191,10 +194,13 @@ __device__ void mma_issuer(const TcParams& kp, uint8_t* sm, Bars* bars, uint32_t
     mbar_wait(&bars->b_full[s], (wcnt / B_STAGES) & 1);
     tc_fence_after_sync();
     const uint32_t b_addr = smem_u32(sm + OFF_B + s * B_STAGE_BYTES);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)(accumulate || k != 0));
-    mma_commit(&bars->b_empty[s]);
+      for (int k = 0; k < 4; ++k)
+        mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)(accumulate || k != 0));
+      mma_commit(&bars->b_empty[s]);
+    }
+    __syncwarp();
     ++wcnt;
   };
   auto acquire_acc = [&]() -> uint32_t {   // TMEM columns of the next stage, once its previous contents are drained
@@ -216,9 +222,11 @@ __device__ void mma_issuer(const TcParams& kp, uint8_t* sm, Bars* bars, uint32_t
         const uint32_t a_addr = smem_u32(sm + OFF_X + slot * CHUNK_BYTES);
         gemm_block(a_addr, d, c != 0);
         gemm_block(a_addr, d + 128, c != 0);
-        mma_commit(&bars->x_empty[slot]);
+        if (elect_one()) mma_commit(&bars->x_empty[slot]);
+        __syncwarp();
       }
-      mma_commit(&bars->acc_full[st & 1]);
+      if (elect_one()) mma_commit(&bars->acc_full[st & 1]);
+      __syncwarp();
       ++st;
     }
     // ---- L1: h0 -> 256 ----
@@ -232,8 +240,11 @@ __device__ void mma_issuer(const TcParams& kp, uint8_t* sm, Bars* bars, uint32_t
         gemm_block(a_addr, d + 128, c != 0);
       }
       ++hcnt;
-      mma_commit(&bars->h_free);            // h0 consumed: the epilogue may write h1 over it
-      mma_commit(&bars->acc_full[st & 1]);
+      if (elect_one()) {
+        mma_commit(&bars->h_free);            // h0 consumed: the epilogue may write h1 over it
+        mma_commit(&bars->acc_full[st & 1]);
+      }
+      __syncwarp();
       ++st;
     }
     // ---- L2: h1 -> 256 (one pass) or 512 (two passes of 256 columns) ----
@@ -248,8 +259,11 @@ __device__ void mma_issuer(const TcParams& kp, uint8_t* sm, Bars* bars, uint32_t
         for (int nb = 0; nb < kp.P2; ++nb) gemm_block(a_addr, d + nb * 128, c != 0);
       }
       if (half == 0) ++hcnt;
-      if (half == kp.halves2 - 1) mma_commit(&bars->h_free);   // h1 consumed: the next tile's h0 may be written
-      mma_commit(&bars->acc_full[st & 1]);
+      if (elect_one()) {
+        if (half == kp.halves2 - 1) mma_commit(&bars->h_free);   // h1 consumed: the next tile's h0 may be written
+        mma_commit(&bars->acc_full[st & 1]);
+      }
+      __syncwarp();
       ++st;
     }
   }
@@ -391,11 +405,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) taps_chain_kernel(const __grid_co
   } else if (warp < E_WARP0 + NUM_E_WARPS) {
     epilogue_warps(kp, &out_map, sm, bars, tmem_base, warp - E_WARP0, lane);
   } else if (warp == W_WARP) {
-    if (lane == 0) weight_producer(kp, sm, bars);
-    __syncwarp();
+    weight_producer(kp, sm, bars);     // whole warp, warp-uniform control flow; an elected lane issues
   } else if (warp == MMA_WARP) {
-    if (lane == 0) mma_issuer(kp, sm, bars, tmem_base);
-    __syncwarp();
+    mma_issuer(kp, sm, bars, tmem_base);
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -230,7 +230,7 @@ __device__ void weight_producer(const EcParams& kp, uint8_t* sm, Bars* bars) {
       for (int nbm = 0; nbm < NBM; ++nbm, ++cnt) {
         const int s = cnt % B_STAGES;
         const uint32_t use = cnt / B_STAGES;
-        if (use > 0) mbar_wait(&bars->b_empty[s], (use - 1) & 1);
+        if (use > 0) mbar_wait_idle(&bars->b_empty[s], (use - 1) & 1);
         const WTile& w0 = kp.wt[c * kp.NB + nbm * SUB];
         const bool two = SUB == 2 && nbm * SUB + 1 < kp.NB;
         const uint32_t bytes1 = two ? kp.wt[c * kp.NB + nbm * SUB + 1].bytes : 0u;
@@ -369,7 +369,7 @@ __device__ void stager(const EcParams& kp, uint8_t* sm, Bars* bars, int pw, int 
       while (rel < r) {
         const uint32_t oldest_v = lds32(vs + (rel % NBAR) * 4);
         if (nvh + U - oldest_v <= R && (int)rel > need_rel) break;
-        mbar_wait(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1);
+        mbar_wait_idle(&bars->stg_empty[rel % NBAR], (rel / NBAR) & 1);
         ++rel;
       }
       if (tid == 0) TR(5, r * 2 + 0);
@@ -566,7 +566,7 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
     PH_T(e1);
     for (int c0 = h * 32; c0 < kp.NB * 128; c0 += 32 * (NUM_EPI_WARPS / 4)) {
       if ((c0 & 127) == h * 32) {   // this warp's first block of a 128-column accumulator block
-        mbar_wait(&bars->acc_full[c0 >> 7], ti & 1);
+        mbar_wait_idle(&bars->acc_full[c0 >> 7], ti & 1);
         tc_fence_after_sync();
       }
       if (lane == 0 && (ew == 0 || ew == 7)) TR(3 + (ew == 7), ti * 8 + (c0 >> 6));

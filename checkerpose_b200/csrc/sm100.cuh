@@ -39,6 +39,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait of a role that runs ahead of or behind the critical path (weight / staging producers, the epilogue between
+// tiles): back off with nanosleep, so that the spin takes neither issue slots nor power from the working warps (the
+// benchmark step runs under the board's power cap: profiles/).
+#ifndef CP_IDLE_SLEEP_NS
+#define CP_IDLE_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (CP_IDLE_SLEEP_NS) __nanosleep(CP_IDLE_SLEEP_NS);
+    if (++spins > (1u << 27)) __trap();
+  }
+}
+
 // One lane of a converged warp (elect.sync): the single-thread instructions (tcgen05.mma / commit, bulk copies) are
 // issued under this predicate while the surrounding control flow stays warp-uniform, so that ptxas keeps their
 // operands in uniform registers (under an `if (lane == 0)` region it wraps every one of them in a broadcast loop).

@@ -140,7 +140,7 @@ __device__ void gather_warps(const TcParams& kp, uint8_t* sm, Bars* bars, int gw
     const uint8_t* gf = reinterpret_cast<const uint8_t*>(p.graph_feat) + ((size_t)b * p.N + n0) * p.ld_gf * 2 + piece * 16;
     for (int c = 0; c < kp.KX; ++c, ++cnt) {
       const uint32_t slot = cnt % NX;
-      if (cnt >= NX) mbar_wait(&bars->x_empty[slot], ((cnt / NX) - 1) & 1);
+      if (cnt >= NX) mbar_wait_idle(&bars->x_empty[slot], ((cnt / NX) - 1) & 1);
       const uint32_t dst = sm_base + OFF_X + slot * CHUNK_BYTES;
       if (c < 4) {
         const int tap_off = (((c & 1) ? p.tap_step : 0) * p.Wp + ((c & 2) ? p.tap_step : 0)) * 128;
@@ -173,7 +173,7 @@ __device__ void weight_producer(const TcParams& kp, uint8_t* sm, Bars* bars) {
     for (int w = 0; w < kp.T; ++w, ++cnt) {
       const int s = cnt % B_STAGES;
       const uint32_t use = cnt / B_STAGES;
-      if (use > 0) mbar_wait(&bars->b_empty[s], (use - 1) & 1);
+      if (use > 0) mbar_wait_idle(&bars->b_empty[s], (use - 1) & 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->b_full[s], kp.wt[w].bytes);
         bulk_g2s(sm + OFF_B + s * B_STAGE_BYTES, kp.wt[w].ptr, kp.wt[w].bytes, &bars->b_full[s]);
@@ -299,7 +299,7 @@ __device__ void epilogue_warps(const TcParams& kp, const CUtensorMap* out_map, u
       const int ncols = k < 2 ? ACC_COLS : kp.P2 * 128;                  // columns of this stage
       const int col0 = k < 2 ? 0 : (k - 2) * ACC_COLS;                   // first output column of the stage
       const uint32_t bias_l = bias_s + (uint32_t)(layer * 256 + col0) * 4;   // layers 0, 1: 256 floats each; layer 2 after them
-      mbar_wait(&bars->acc_full[slot], (st >> 1) & 1);
+      mbar_wait_idle(&bars->acc_full[slot], (st >> 1) & 1);
       tc_fence_after_sync();
       if (k < 2) {   // the H buffer must be free: h1 of the previous tile (k = 0) / h0 of this tile (k = 1) consumed
         if (hfree > 0) mbar_wait(&bars->h_free, (hfree - 1) & 1);

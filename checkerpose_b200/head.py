@@ -501,12 +501,15 @@ def _stage_ctx(net, ref, obj_ids, B, dev, base_ctx):
         return base_ctx
     ctx = graph_ctx(blocks[0]._knn, obj_ids, B, dev)
     if base_ctx is not None and ctx.plan is not base_ctx.plan:
+        # checked once per pair of plans (torch.equal synchronises the stream: a check per step stalled the host three
+        # times per step)
         key = (id(ctx.plan), id(base_ctx.plan))
         ok = net.__dict__.setdefault("_cp_perm_ok", {})
         if key not in ok:
-            ok.clear()
-            ok[key] = bool(torch.equal(ctx.plan.perm, base_ctx.plan.perm))
-        if not ok[key]:
+            if len(ok) > 64:
+                ok.clear()
+            ok[key] = (bool(torch.equal(ctx.plan.perm, base_ctx.plan.perm)), ctx.plan, base_ctx.plan)   # keeps the ids alive
+        if not ok[key][0]:
             raise RuntimeError("the kNN graphs of one net must be built from the same keypoints (their plan orders differ)")
     return ctx
 

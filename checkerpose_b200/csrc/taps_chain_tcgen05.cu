@@ -38,9 +38,15 @@ constexpr int W_WARP = 12, MMA_WARP = 13;
 constexpr int NUM_WARPS = 16;   // two idle warps: 512 threads leave 128 registers per thread
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int CHUNK_BYTES = TILE_M * 128;   // 128 rows x 64 bf16
-constexpr int NX = 4;                       // gather ring slots
+#ifndef CP_K3_NX
+#define CP_K3_NX 4
+#endif
+#ifndef CP_K3_BSTAGES
+#define CP_K3_BSTAGES 4
+#endif
+constexpr int NX = CP_K3_NX;                // gather ring slots
 constexpr int NH = 4;                       // chunks of h0 / h1 (256 channels)
-constexpr int B_STAGES = 4, B_STAGE_BYTES = 128 * 128;
+constexpr int B_STAGES = CP_K3_BSTAGES, B_STAGE_BYTES = 128 * 128;
 constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: a tile of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores
 constexpr int BIAS_FLOATS = 1024;           // 256 + 256 + 512
 constexpr int ACC_COLS = 256;

@@ -253,3 +253,40 @@ def test_lm_per_sample_graph_matches_single_object_nets():
             else:
                 # cuDNN may pick different fp32 algorithms for different batch sizes: north_star's 1e-3 relative, not bit-equality
                 assert torch.allclose(a[rows.cuda()], b, rtol=1e-3, atol=1e-3 * float(b.abs().max()))
+
+
+@pytest.mark.parametrize("N,K", [(512, 8), (512, 32), (1024, 16), (512, 40)])
+def test_lm_head_keypoint_and_k_sweep_fp32_vs_oracle(N, K):
+    """BASELINE.json configs[4]: LM single-model net (15 graphs, per-RoI selection by obj_ids), keypoint-count and
+    graph_k sweep, fp32 mode against the CPU oracle (which is pinned to the reference by tests/test_oracle_golden.py):
+    floats within 1e-3 of scale, ids exact outside the 1e-4 logit band (cascade-aware)."""
+    from checkerpose_b200 import head
+    from checkerpose_b200.model import init_lm, pipeline_lm
+    from checkerpose_b200.model.backbone import FeatureListBackbone
+    from oracle import checkerpose_oracle as orc
+    B = 3
+    g = torch.Generator().manual_seed(1000 + N + K)
+    p3d_all = torch.cat([syn.p3d_normed_tensor(syn.load_fps_xyz("lm", o, N)) for o in range(1, 16)], dim=0)
+    sd = syn.synthetic_state_dict(syn.head_param_spec(N), g)
+    feats = syn.synthetic_features(B, g)
+    obj_ids = torch.tensor([13, 1, 6])
+    idx_ref = orc.knn(p3d_all, K)
+    ref = orc.pose_head(feats, sd, idx_ref, [idx_ref] * 3, N, obj_ids=obj_ids)
+    head.set_compute_dtype(torch.float32)
+    dev = "cuda"
+    inet = init_lm.InitNet_GNN(npoint=N, p3d_normed=p3d_all.to(dev), res_log2=3, backbone_name="hrnet_w18", pretrain_backbone=False,
+                               num_conv1x1=1, max_batch_size=64, num_graph_module=2, graph_k=K, graph_leaky_slope=0.2,
+                               img_backbone=FeatureListBackbone())
+    net = pipeline_lm.PoseNet_GNNskip(inet, npoint=N, p3d_normed=p3d_all.to(dev), res_log2=6, num_filters=256, max_batch_size=64,
+                                      query_dims=None, local_k=2, leaky_slope=0.01, num_graph_module=3, graph_k=K,
+                                      graph_leaky_slope=0.2, query_type="mlp")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    out = run_net(net, feats, p3d_all, obj_ids, True)
+    for a, b in zip(out[:4], ref[:4]):
+        err = float((a.cpu() - b).abs().max() / b.abs().max())
+        assert err < 1e-3, err
+    ok, frac = code_agreement(out[4].cpu().numpy(), out[5].cpu().numpy(), ref[4].numpy(), ref[5].numpy(),
+                              ref[1].numpy(), ref[2].numpy(), ref[0].numpy(), 1e-4)
+    print(f"N={N} K={K}: cell agreement {frac:.5f}")
+    assert ok and frac >= 0.999

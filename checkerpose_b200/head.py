@@ -494,6 +494,83 @@ def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, ctx, dtype)
     return logits, feat
 
 
+# --------------------------------------------------------------------------------------------------
+# ablation variant without progressive refinement (pipeline_lm.py:286-339, 430-517)
+# --------------------------------------------------------------------------------------------------
+def mlp_node_major(mods, x_nm, dtype, out_f32=False):
+    """nn.Sequential of Linear / LeakyReLU (get_MLP_leakyReLU_layers) on node-major x (B,N,C) of ``dtype``.
+    bf16: chain kernel, up to three layers per launch; ``out_f32`` -> (B,N,>=nout padded to 16) f32 logits."""
+    mods = list(mods)
+    layers = []
+    i = 0
+    while i < len(mods):
+        act = i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU)
+        layers.append((mods[i], act, float(mods[i + 1].negative_slope) if act else 0.0))
+        i += 2 if act else 1
+    B, N, _ = x_nm.shape
+    if dtype == torch.float32:
+        x = x_nm
+        for lin, act, slope in layers:
+            pl = prepared_linear(lin, dtype)
+            x = ops.linear_f32(x, pl.w, pl.b, act, slope)
+        return x
+    x = x_nm
+    for j0 in range(0, len(layers), 3):
+        grp = layers[j0:j0 + 3]
+        pls = [prepared_linear(lin, dtype) for lin, _, _ in grp]
+        if not all(_chain_ok(pl.kin) for pl in pls):
+            raise RuntimeError("bf16 MLP supports layer inputs in {64,128,256}; use float32 mode for other shapes")
+        cl = [ops.chain_layer(pl.packed, pl.b, pl.kin, pl.nout, act, slope) for pl, (_, act, slope) in zip(pls, grp)]
+        last = j0 + 3 >= len(layers)
+        if last and out_f32:
+            out = torch.empty((B, N, (pls[-1].nout + 15) // 16 * 16), dtype=torch.float32, device=x.device)
+            ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x, layers=cl, out=out, out_mode=ops.OUT_F32, n_valid=pls[-1].nout)
+        else:
+            out = torch.empty((B, N, pls[-1].nout), dtype=torch.bfloat16, device=x.device)
+            ops.chain_fwd(prologue=ops.PRO_LOAD, B=B, N=N, src=x, layers=cl, out=out, out_mode=ops.OUT_BF16)
+        x = out
+    return x
+
+
+def abwoprog_refine_node_major(ref, gfeat_nm, ctx, dtype):
+    """Refine_moduleGNN_ABwoProg.forward (pipeline_lm.py:324-339) on plan-order node tensors: MLP on the graph
+    feature, then the EdgeConv stack."""
+    _require_eval(ref)
+    h = mlp_node_major(ref.pre_graph_module, gfeat_nm, dtype)
+    for blk in ref.pre_query_block:
+        h = edgeconv_node_major(blk, h, ctx, dtype)
+    return h
+
+
+def abwoprog_head_forward(net, img_feats, obj_ids, stage=None, dtype=None):
+    """PoseNet_GNNskip_ABwoProg.forward after the backbone (pipeline_lm.py:484-517) -> the reference's 6-tuple."""
+    dtype = dtype or get_compute_dtype()
+    _require_eval(net)
+    nact = net.num_refine_steps if stage is None else stage
+    feat_last = img_feats[-1]
+    B, dev = feat_last.shape[0], feat_last.device
+    _, gfeat, ctx = init_head_node_major(net.init_net, feat_last, obj_ids, dtype)
+    img_feat = feat_last
+    for i in range(nact):
+        img_feat = image_block(net.up_net[i], img_feat, dtype, skip=img_feats[-i - 1] if i > 0 else None)
+        sctx = _stage_ctx(net, net.refine_net[i], obj_ids, B, dev, ctx)
+        if ctx is None and sctx is not None:      # init net without graph modules: enter the plan order here
+            gfeat = sctx.to_plan(gfeat)
+        ctx = sctx if sctx is not None else ctx
+        gfeat = abwoprog_refine_node_major(net.refine_net[i], gfeat, ctx, dtype)
+    seg = image_block(net.seg_block, img_feat, dtype).float().contiguous()
+    nb = net.num_bits
+    bits = mlp_node_major(net.query_block.mlps, gfeat, dtype, out_f32=True)[:, :, :nb].contiguous()
+    if ctx is not None:
+        bits = ctx.to_keypoints(bits)
+    bits = bits.permute(0, 2, 1).contiguous()      # (B, #bits, N)
+    L = net.res_log2
+    roi_bit, x_bits, y_bits = bits[:, 0:1], bits[:, 1:L + 1], bits[:, L + 1:]
+    x_id = ops.bits_to_id(x_bits, 1, binarize=True, thr=0.0)     # from_code_prob_to_id: sigmoid(x) > 0.5 == x > 0
+    y_id = ops.bits_to_id(y_bits, 1, binarize=True, thr=0.0)
+    return roi_bit, x_bits, y_bits, seg, x_id, y_id
+
+
 def _stage_ctx(net, ref, obj_ids, B, dev, base_ctx):
     """GraphCtx of a refine stage; all graphs of one net must share the keypoint renumbering."""
     blocks = list(ref.pre_query_block)

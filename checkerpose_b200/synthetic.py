@@ -150,6 +150,33 @@ def head_param_spec(npoint: int, res_log2: int = 6, num_filters: int = 256,
     return spec
 
 
+def abwoprog_param_spec(npoint: int, res_log2: int = 6, num_filters: int = 256, init_num_graph_module: int = 2,
+                        num_graph_module: int = 3, query_dims=None, seg_output_dim: int = 2):
+    """Spec of ``PoseNet_GNNskip_ABwoProg(InitNet_GNN(...))`` (pipeline_lm.py:430-517): the refine stages only refine the
+    graph feature (no image sampling, no per-stage query); ONE query MLP emits all 2*res_log2+1 bits at the end."""
+    qd = (num_filters, 256, 64) if query_dims is None else tuple(query_dims)
+    full = head_param_spec(npoint, res_log2, num_filters, init_num_graph_module, num_graph_module, 2, query_dims, seg_output_dim)
+    spec = [e for e in full if not e[0].startswith("refine_net.") and not e[0].startswith("seg_block.")]
+    for i in range(res_log2 - 3):
+        r = f"refine_net.{i}."
+        gdim = 64 if i == 0 else qd[0]
+        spec.append((r + "pre_graph_module.0.weight", (qd[0], gdim), "w", gdim))
+        spec.append((r + "pre_graph_module.0.bias", (qd[0],), "b", None))
+        spec.append((r + "pre_graph_module.2.weight", (qd[0], qd[0]), "w", qd[0]))
+        spec.append((r + "pre_graph_module.2.bias", (qd[0],), "b", None))
+        ngm = num_graph_module if isinstance(num_graph_module, int) else num_graph_module[i]
+        for j in range(ngm):
+            spec.append((r + f"pre_query_block.{j}.conv.0.weight", (qd[0], 2 * qd[0], 1, 1), "w", 2 * qd[0]))
+            spec += [(k, sh, kind, None) for k, sh, kind in _bn_keys(r + f"pre_query_block.{j}.conv.1", qd[0])]
+    spec.append(("seg_block.weight", (seg_output_dim, num_filters, 1, 1), "w", num_filters))
+    spec.append(("seg_block.bias", (seg_output_dim,), "b", None))
+    dims = qd + (2 * res_log2 + 1,)
+    for j in range(1, len(dims)):
+        spec.append((f"query_block.mlps.{2 * (j - 1)}.weight", (dims[j], dims[j - 1]), "w", dims[j - 1]))
+        spec.append((f"query_block.mlps.{2 * (j - 1)}.bias", (dims[j],), "b", None))
+    return spec
+
+
 def synthetic_state_dict(spec, gen: torch.Generator) -> "OrderedDict[str, torch.Tensor]":
     """He-normal weights, small biases, randomised BN stats with 25 % negative gammas."""
     sd = OrderedDict()

@@ -237,6 +237,33 @@ def pose_head(img_feats, sd, init_knn_idx, refine_knn_idx, npoint, res_log2=6, l
 # correspondences: first half of from_id_to_pose (test_network_with_test_data.py:50-66) with the
 # RoI grid of bop_dataset_pytorch.py:266-269,223-235,359.
 # ------------------------------------------------------------------------------------------
+def pose_head_abwoprog(img_feats, sd, init_knn_idx, refine_knn_idx, npoint, res_log2=6, leaky_slope=0.01,
+                       init_num_graph_module=2, num_graph_module=3, init_graph_slope=0.2, graph_slope=0.2,
+                       obj_ids=None, stage=None):
+    """PoseNet_GNNskip_ABwoProg.forward after the backbone (pipeline_lm.py:484-517) with
+    Refine_moduleGNN_ABwoProg.forward (pipeline_lm.py:324-339): the stages refine the graph feature only, one
+    MLP_QueryNet emits all 2*res_log2+1 logits at the end, ids are the MSB-first decode of the thresholded bits."""
+    nact = (res_log2 - 3) if stage is None else stage
+    _, graph_feat = init_head(img_feats[-1], sd, init_knn_idx, npoint, init_num_graph_module, init_graph_slope, obj_ids)
+    img_feat = img_feats[-1]
+    for i in range(nact):
+        if i > 0:
+            img_feat = torch.cat([img_feat, img_feats[-i - 1]], dim=1)                      # :498
+        img_feat = upsample_module(img_feat, sd, f"up_net.{i}.", is_convtrans=(i == 0))     # :499
+        prefix = f"refine_net.{i}."
+        lf = mlp_leaky(graph_feat.permute(0, 2, 1), sd, prefix + "pre_graph_module.", 2, leaky_slope,
+                       last_act=True).permute(0, 2, 1)                                      # :332-334
+        idx = _select_graph(refine_knn_idx[i], obj_ids)
+        ngm = num_graph_module if isinstance(num_graph_module, int) else num_graph_module[i]
+        for j in range(ngm):
+            lf = _sg_from_sd(lf, idx, sd, f"{prefix}pre_query_block.{j}.", graph_slope)     # :337-338
+        graph_feat = lf
+    seg = F.conv2d(img_feat, sd["seg_block.weight"], sd["seg_block.bias"])                  # :502
+    bits = mlp_leaky(graph_feat.permute(0, 2, 1), sd, "query_block.mlps.", 3, leaky_slope, last_act=False).permute(0, 2, 1)
+    roi_bit, x_bits, y_bits = bits[:, 0:1], bits[:, 1:res_log2 + 1], bits[:, res_log2 + 1:]  # :507-509
+    return roi_bit, x_bits, y_bits, seg, from_code_prob_to_id(x_bits), from_code_prob_to_id(y_bits)
+
+
 def roi_xy_ori(bbox, size):
     """bbox (4,) [x,y,w,h] -> (size,size,2) grid: (x + u*w/size, y + v*h/size)."""
     bbox = np.asarray(bbox, dtype=np.float64)

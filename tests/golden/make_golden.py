@@ -325,8 +325,41 @@ def golden_heads():
              checksum_feat=np.array([syn.tensor_checksum(f) for f in feats]).sum())
 
 
+ABWOPROG_CASE = ("lm", tuple(range(1, 16)), 128, 3, 1234 + 7)   # must mirror tests/helpers.py::ABWOPROG_CASE
+
+
+def abwoprog_case_inputs():
+    ds, objs, N, B, seed = ABWOPROG_CASE
+    g = torch.Generator().manual_seed(seed)
+    p3d = torch.cat([syn.p3d_normed_tensor(syn.load_fps_xyz(ds, o, N)) for o in objs], dim=0)
+    sd = syn.synthetic_state_dict(syn.abwoprog_param_spec(N), g)
+    feats = syn.synthetic_features(B, g)
+    obj_ids = torch.tensor([objs[(i * 5 + 2) % len(objs)] for i in range(B)])
+    return p3d, sd, feats, obj_ids
+
+
+def golden_abwoprog():
+    """PoseNet_GNNskip_ABwoProg (pipeline_lm.py:430-517), the ablation net test_lm.py:173-176 builds."""
+    ds, objs, N, B, seed = ABWOPROG_CASE
+    p3d, sd, feats, obj_ids = abwoprog_case_inputs()
+    init = ref_init_lm.InitNet_GNN(npoint=N, p3d_normed=p3d, res_log2=3, backbone_name="hrnet_w18", pretrain_backbone=False,
+                                   num_conv1x1=1, max_batch_size=8, num_graph_module=2, graph_k=20, graph_leaky_slope=0.2)
+    net = ref_pipe_lm.PoseNet_GNNskip_ABwoProg(init, npoint=N, p3d_normed=p3d, res_log2=6, num_filters=256, max_batch_size=8,
+                                               query_dims=None, local_k=2, leaky_slope=0.01, num_graph_module=3, graph_k=20,
+                                               graph_leaky_slope=0.2, query_type="mlp")
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    net.eval()
+    roi, xb, yb, seg, xid, yid = net(feats, p3d[obj_ids - 1], obj_ids)
+    save("head_abwoprog_lm15_n128_b3", roi_bit=roi, x_bits=xb, y_bits=yb, seg=seg, x_id=xid, y_id=yid, obj_ids=obj_ids,
+         checksum_sd=np.array([syn.tensor_checksum(v) for v in sd.values() if v.dtype.is_floating_point]).sum(),
+         checksum_feat=np.array([syn.tensor_checksum(f) for f in feats]).sum())
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "modules", "decode", "corr", "heads"]
+    which = sys.argv[1:] or ["knn", "modules", "decode", "corr", "heads", "abwoprog"]
+    if "abwoprog" in which:
+        golden_abwoprog()
     if "knn" in which:
         golden_knn()
     if "modules" in which:

@@ -29,6 +29,20 @@ def head_case_inputs(name):
     return p3d, sd, feats, obj_ids
 
 
+# must mirror tests/golden/make_golden.py::ABWOPROG_CASE
+ABWOPROG_CASE = ("lm", tuple(range(1, 16)), 128, 3, 1234 + 7)
+
+
+def abwoprog_case_inputs():
+    ds, objs, N, B, seed = ABWOPROG_CASE
+    g = torch.Generator().manual_seed(seed)
+    p3d = torch.cat([syn.p3d_normed_tensor(syn.load_fps_xyz(ds, o, N)) for o in objs], dim=0)
+    sd = syn.synthetic_state_dict(syn.abwoprog_param_spec(N), g)
+    feats = syn.synthetic_features(B, g)
+    obj_ids = torch.tensor([objs[(i * 5 + 2) % len(objs)] for i in range(B)])
+    return p3d, sd, feats, obj_ids
+
+
 def check_head_checksums(gold, sd, feats):
     cs_sd = np.array([syn.tensor_checksum(v) for v in sd.values() if v.dtype.is_floating_point]).sum()
     cs_f = np.array([syn.tensor_checksum(f) for f in feats]).sum()

@@ -119,3 +119,19 @@ def test_full_head(golden, name):
     for a, k in ((roi, "roi_bit"), (xb, "x_bits"), (yb, "y_bits"), (seg, "seg"), (inter["graph_feat"][0], "init_graph_feat")):
         assert torch.allclose(a, torch.from_numpy(g[k]), rtol=1e-4, atol=1e-4), k
     assert xid.dtype == torch.int64 and xb.shape == (B, 6, N) and seg.shape == (B, 2, 64, 64)
+
+
+def test_abwoprog_head(golden):
+    """oracle.pose_head_abwoprog vs the unmodified PoseNet_GNNskip_ABwoProg (pipeline_lm.py:430-517)."""
+    from helpers import ABWOPROG_CASE, abwoprog_case_inputs
+    g = golden("head_abwoprog_lm15_n128_b3")
+    ds, objs, N, B, seed = ABWOPROG_CASE
+    p3d, sd, feats, obj_ids = abwoprog_case_inputs()
+    check_head_checksums(g, sd, feats)
+    assert np.array_equal(obj_ids.numpy(), g["obj_ids"])
+    idx = orc.knn(p3d, 20)
+    roi, xb, yb, seg, xid, yid = orc.pose_head_abwoprog(feats, sd, idx, [idx] * 3, N, obj_ids=obj_ids)
+    assert np.array_equal(xid.numpy(), g["x_id"]) and np.array_equal(yid.numpy(), g["y_id"])
+    for a, k in ((roi, "roi_bit"), (xb, "x_bits"), (yb, "y_bits"), (seg, "seg")):
+        assert torch.allclose(a, torch.from_numpy(g[k]), rtol=1e-4, atol=1e-4), k
+    assert xb.shape == (B, 6, N) and yb.shape == (B, 6, N) and xid.dtype == torch.int64

@@ -334,3 +334,43 @@ def test_abwoprog_head_vs_reference_golden(golden, dtype):
             scale = np.abs(g[k]).max()
             assert np.sqrt((d ** 2).mean()) < 3e-2 * scale and np.abs(d).max() < 6e-2 * scale, (k, np.abs(d).max() / scale)
         print("bf16 ABwoProg cell agreement", float(((xid.cpu().numpy() == g["x_id"]) & (yid.cpu().numpy() == g["y_id"])).mean()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("init_gm,ref_gm", [(0, 0), (2, 0), (0, 3)])
+def test_head_without_edgeconv_configs(dtype, init_gm, ref_gm):
+    """The shipped woEdgeConv / init_gnn0 configs (config/lm/*woEdgeConv*.txt:17,25: num_graph_module = 0 in the init net
+    and / or the refine stages) against the CPU oracle."""
+    from checkerpose_b200 import head
+    from checkerpose_b200.model import init, pipeline
+    from checkerpose_b200.model.backbone import FeatureListBackbone
+    from oracle import checkerpose_oracle as orc
+    N, B = 256, 2
+    g = torch.Generator().manual_seed(500 + 10 * init_gm + ref_gm)
+    p3d = syn.p3d_normed_tensor(syn.load_fps_xyz("lmo", 5, N))
+    sd = syn.synthetic_state_dict(syn.head_param_spec(N, init_num_graph_module=init_gm, num_graph_module=ref_gm), g)
+    feats = syn.synthetic_features(B, g)
+    idx = orc.knn(p3d, 20)
+    ref = orc.pose_head(feats, sd, idx, [idx] * 3, N, init_num_graph_module=init_gm, num_graph_module=ref_gm)
+    dev = "cuda"
+    inet = init.InitNet_GNN(npoint=N, p3d_normed=p3d.to(dev), res_log2=3, backbone_name="hrnet_w18", pretrain_backbone=False,
+                            num_conv1x1=1, max_batch_size=8, num_graph_module=init_gm, graph_k=20, img_backbone=FeatureListBackbone())
+    net = pipeline.PoseNet_GNNskip(inet, npoint=N, p3d_normed=p3d.to(dev), res_log2=6, num_filters=256, max_batch_size=8,
+                                   local_k=2, leaky_slope=0.01, num_graph_module=ref_gm, graph_k=20)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    head.set_compute_dtype(dtype)
+    try:
+        out = run_net(net, feats, p3d, None, False)
+    finally:
+        head.set_compute_dtype(torch.float32)
+    if dtype == torch.float32:
+        for a, b in zip(out[:4], ref[:4]):
+            assert float((a.cpu() - b).abs().max() / b.abs().max()) < 1e-3
+        ok, frac = code_agreement(out[4].cpu().numpy(), out[5].cpu().numpy(), ref[4].numpy(), ref[5].numpy(),
+                                  ref[1].numpy(), ref[2].numpy(), ref[0].numpy(), 1e-4)
+        assert ok and frac >= 0.999
+    else:
+        # init-stage logits (no cascade yet) within the chained-layer bf16 budget
+        for a, b in ((out[0], ref[0]), (out[1][:, :3], ref[1][:, :3]), (out[2][:, :3], ref[2][:, :3])):
+            assert float((a.cpu() - b).abs().max() / b.abs().max()) < BF16_MAX

@@ -92,27 +92,22 @@ __device__ __forceinline__ uint32_t f2_to_bf2(float lo, float hi) {
 
 // ---- prologues: all 256 threads fill A chunks [0, C/64) for the 128 rows of the tile -----------------
 
-// rows of a node-major bf16 tensor; C in {64,128,256}
+// rows of a node-major bf16 tensor; C in {64,128,256}.  cp.async (LDGSTS) straight into the swizzled operand layout,
+// zero-filled beyond rows_valid: all of a thread's 16-byte pieces (up to 16 at C = 256) are in flight at once -- one
+// memory round trip per tile instead of the four of the register-staged version (0.224 -> see DESIGN.md section 8).
 __device__ __forceinline__ void fill_rows(uint8_t* A, const bf16* src, int ld, int C, int64_t row0, int rows_valid) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cpr = C >> 3;  // 16-byte chunks per row
   const int rpi = 32 / cpr;
   const int sub = lane / cpr, chunk = lane - sub * cpr;
-  // four rows in flight per thread: the loads of a batch are issued before its stores
-  for (int r0 = warp * rpi + sub; r0 < TILE_M; r0 += 4 * NWARPS * rpi) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int r = r0 + u * NWARPS * rpi;
-      v[u] = make_uint4(0, 0, 0, 0);
-      if (r < rows_valid) v[u] = ldg_nc_v4(src + (row0 + r) * ld + chunk * 8);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int r = r0 + u * NWARPS * rpi;
-      if (r < TILE_M) *reinterpret_cast<uint4*>(A + a_offset(chunk >> 3, r, chunk & 7)) = v[u];
-    }
+  const uint32_t a_s = sm100::smem_u32(A);
+  for (int r = warp * rpi + sub; r < TILE_M; r += NWARPS * rpi) {
+    const bool ok = r < rows_valid;
+    const void* g = src + (ok ? (row0 + r) * ld + chunk * 8 : 0);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_s + a_offset(chunk >> 3, r, chunk & 7)), "l"(g), "r"(ok ? 16u : 0u) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // EdgeConv aggregation; Co in {64,128,256}

@@ -2,31 +2,30 @@
 //
 // Replaces StaticGraph_module.forward of checkerpose/model/pipeline.py:45-59 (get_graph_feature :27-40 +
 // Conv2d 1x1 + BatchNorm2d + LeakyReLU + max over K) in the factored form of cp_fold_edgeconv, fused with
-// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 28 warps (7 warpgroups) per SM; the unit of work ("round") is one 64-channel
-// slice of one tile of 128 plan-order nodes:
+// the GEMM of the layer that consumes the aggregated feature.  One persistent CTA of 32 warps (8 warpgroups) per SM;
+// the unit of work ("round") is one 64-channel slice of one tile of 128 plan-order nodes:
 //
-//   warps 0-15  aggregators.  They are their own staging producers: every thread copies its share of the tile's
-//               DISTINCT neighbour row slices (plan.ulist, ~245 rows x 128 B instead of 128 x K gathered rows) from
-//               the [P|Q] table into a shared-memory ring with cp.async (LDGSTS), up to LOOKAHEAD rounds ahead of
-//               the round it reduces.  The ring bookkeeping is a pure function of the plan's list lengths, so the
-//               warps replicate it (a few words of shared memory per warp) and agree on every round's position
-//               without talking to each other.  To reduce, a quarter-warp owns one node PAIR of the plan: it takes
-//               the max over the rows the two nodes share once, then over the rest of each (40 - C row reads of
-//               128 bits per lane instead of 40), adds the nodes' own Q slices, applies LeakyReLU and writes the
-//               bf16 A operand slice straight into the SWIZZLE_128B layout tcgen05.mma reads.  The plan's
-//               overlap-sorted pair groups rotate over the warps from slice to slice, so every warp reads about
-//               the same number of rows per tile;
+//   warps 0-15  aggregators.  A quarter-warp owns one node PAIR of the plan: it takes the max over the staged rows the
+//               two nodes share once, then over the rest of each (40 - C row reads of 128 bits per lane instead of 40),
+//               adds the nodes' own Q slices, applies LeakyReLU and writes the bf16 A operand slice straight into the
+//               SWIZZLE_128B layout tcgen05.mma reads.  The plan's overlap-sorted pair groups rotate over the warps
+//               from slice to slice, so every warp reads about the same number of rows per tile;
 //   warps 16-23 epilogue (two warps per TMEM lane quarter, every second 32-column block each): TMEM -> registers ->
 //               bias / LeakyReLU -> bf16 -> a swizzled shared-memory tile -> global with TMA tensor stores (or fp32
-//               logits with plain stores);
+//               logits with plain stores); waits for / releases the accumulator per 128-column block;
 //   warp 24     weight producer: streams the packed weight tiles (16 KB) with cp.async.bulk (TMA engine);
-//   warp 25     one thread issues tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete;
-//   warps 26-27 idle (they complete the warpgroup).
-// The register file is re-divided with setmaxnreg: 88 registers per aggregator thread, 64 per epilogue thread, 24 for
-// the control warpgroup (the kernel is launched at 72).
+//   warp 25     MMA issuer: tcgen05.mma (M=128, N<=128, K=16) slice by slice as A slices complete; warp-uniform loop,
+//               the instructions are issued under elect.sync (see mma_issuer: this warp is the critical path);
+//   warps 26-27 idle (they complete the control warpgroup);
+//   warps 28-31 stagers: copy every round's DISTINCT neighbour row slices (plan.ulist, ~245 rows x 128 B instead of
+//               128 x K gathered rows) from the [P|Q] table into a shared-memory ring with cp.async (LDGSTS) and
+//               signal the round with cp.async.mbarrier.arrive.noinc (asynchronous: they never wait for their own
+//               copies and run ahead as far as the ring has room).  Ring positions are a pure function of the plan's
+//               list lengths: stagers and aggregators recompute them and never exchange positions.
+// The register file is re-divided with setmaxnreg (REGS_* below; the kernel is launched at 64 registers per thread).
 //
 // The aggregation of tile i+1 overlaps the MMAs and the epilogue of tile i; every hand-off is an mbarrier.
-// The kernel is bound by the shared-memory port.
+// What bounds the kernel: DESIGN.md section 5.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -52,11 +51,15 @@ constexpr int NUM_STG_WARPS = 4;
 constexpr int STG_THREADS = NUM_STG_WARPS * 32;
 constexpr int NUM_WARPS = STG_WARP0 + NUM_STG_WARPS;
 #ifndef CP_REGS_AGG
-#define CP_REGS_AGG 80
-#define CP_REGS_EPI 56
+// measured (ms per launch, 256->512 / 256->256 + a_out): 72/64/56/40 0.623 / 0.600; 80/56/56/24 0.655 / 0.601;
+// 80/56/48/32 0.632 / 0.601; 80/48/56/40 0.668 / 0.607; 80/56/40/40 0.663 / 0.688 (the stagers need 56, the MMA warp
+// spills below 40, the epilogue slows below 64)
+#define CP_REGS_AGG 72
+#define CP_REGS_EPI 64
 #define CP_REGS_STG 56
+#define CP_REGS_CTRL 40
 #endif
-constexpr int REGS_AGG = CP_REGS_AGG, REGS_EPI = CP_REGS_EPI, REGS_CTRL = 24, REGS_STG = CP_REGS_STG;   // the kernel is launched at 64
+constexpr int REGS_AGG = CP_REGS_AGG, REGS_EPI = CP_REGS_EPI, REGS_CTRL = CP_REGS_CTRL, REGS_STG = CP_REGS_STG;   // the kernel is launched at 64
 static_assert(NUM_WARPS == 32 && NUM_AGG_WARPS * REGS_AGG + NUM_EPI_WARPS * REGS_EPI + 4 * REGS_CTRL + NUM_STG_WARPS * REGS_STG <= NUM_WARPS * 64,
               "register budget");
 constexpr int NTHREADS = NUM_WARPS * 32;
@@ -244,64 +247,64 @@ __device__ void weight_producer(const EcParams& kp, uint8_t* sm, Bars* bars) {
   }
 }
 
+// The MMA warp is the kernel's critical path: every instruction between two tcgen05.mma costs
+// tile time, so the loop keeps running ring positions / parities / descriptor words in registers (no modulo, no
+// constant-bank table look-ups, no 64-bit descriptor rebuild per MMA) and issues under elect.sync.
 __device__ void mma_issuer(const EcParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base) {
-  uint32_t cnt = 0, it = 0;
-  int ti = 0;
-#ifdef CP_PROFILE_PHASES
-  long long ph[12] = {0};
-#endif
-  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++ti) {
-    for (int c = 0; c < kp.KC; ++c, ++it) {
-      const uint32_t ab = it % A_BUFS;
-      PH_T(m2);
-      mbar_wait(&bars->a_full[ab], (it / A_BUFS) & 1);
-      PH_T(m3);
-      PH_ADD(9, m2, m3);
-      TR(0, it * 4 + 0);
-      tc_fence_after_sync();
-      const uint32_t a_addr = smem_u32(sm + OFF_A + ab * A_BUF_BYTES);
-      constexpr int SUB = MMA_N / 128;
-      const int NBM = (kp.NB + SUB - 1) / SUB;
-      for (int nbm = 0; nbm < NBM; ++nbm, ++cnt) {
-        const int s = cnt % B_STAGES;
-        PH_T(m4);
-        mbar_wait(&bars->b_full[s], (cnt / B_STAGES) & 1);
-        PH_T(m5);
-        PH_ADD(10, m4, m5);
+  static_assert(MMA_N == 128, "one 128-row weight tile per stage");
+  const uint32_t a_lo0 = smem_desc_lo(smem_u32(sm + OFF_A)), b_lo0 = smem_desc_lo(smem_u32(sm + OFF_B));
+  const uint32_t a_full0 = smem_u32(&bars->a_full[0]), a_empty0 = smem_u32(&bars->a_empty[0]);
+  const uint32_t b_full0 = smem_u32(&bars->b_full[0]), b_empty0 = smem_u32(&bars->b_empty[0]);
+  const uint32_t acc_full0 = smem_u32(&bars->acc_full[0]), acc_empty0 = smem_u32(&bars->acc_empty[0]);
+  const int KC = kp.KC, NB = kp.NB;
+  const uint32_t idesc_full = make_idesc_bf16_m128(128);
+  const uint32_t idesc_last = make_idesc_bf16_m128((uint32_t)(kp.npad - (NB - 1) * 128));
+  uint32_t ab = 0, a_par = 0;     // A slice ring position and the parity to wait for
+  uint32_t bs = 0, b_par = 0;     // weight stage ring position and parity
+  uint32_t acc_par = 0;           // parity of acc_empty to wait for (flips per tile; nothing to wait for on the first)
+  bool first_tile = true;
+  auto wait_s = [](uint32_t bar_s, uint32_t parity) {   // mbarrier wait on a shared-space address
+    uint32_t ok, spins = 0;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar_s), "r"(parity) : "memory");
+      if (!ok && ++spins > (1u << 27)) __trap();   // a broken pipeline traps instead of hanging the GPU box
+    } while (!ok);
+  };
+  auto commit_s = [](uint32_t bar_s) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s) : "memory");
+  };
+  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x) {
+    for (int c = 0; c < KC; ++c) {
+      wait_s(a_full0 + ab * 8, a_par);
+      const uint32_t a_lo = a_lo0 + ab * (A_BUF_BYTES >> 4);
+      const bool last_slice = c == KC - 1;
+      for (int nb = 0; nb < NB; ++nb) {
+        wait_s(b_full0 + bs * 8, b_par);
+        if (c == 0 && !first_tile) wait_s(acc_empty0 + nb * 8, acc_par);   // the previous tile's columns are drained
         tc_fence_after_sync();
-        const uint32_t b_addr = smem_u32(sm + OFF_B + s * B_STAGE_BYTES);
-        const int nb0 = nbm * SUB, nb1 = min(nb0 + SUB, kp.NB);     // 128-column accumulator blocks this MMA covers
-        uint32_t ncols = 0;
-        for (int nb = nb0; nb < nb1; ++nb) ncols += kp.wt[c * kp.NB + nb].bytes >> 7;
-        const uint32_t idesc = make_idesc_bf16_m128(ncols);
-        const uint32_t d = tmem_base + (uint32_t)(nb0 * 128);
-        if (c == 0 && ti > 0) {
-          PH_T(m0);
-          for (int nb = nb0; nb < nb1; ++nb) mbar_wait(&bars->acc_empty[nb], (ti - 1) & 1);  // the epilogue of the previous tile has drained these columns
-          PH_T(m1);
-          PH_ADD(8, m0, m1);
-          tc_fence_after_sync();
-        }
+        const uint32_t b_lo = b_lo0 + bs * (B_STAGE_BYTES >> 4);
+        const uint32_t idesc = nb == NB - 1 ? idesc_last : idesc_full;
+        const uint32_t d = tmem_base + (uint32_t)(nb * 128);
         if (elect_one()) {
 #ifndef CP_KO_MMA
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((c | k) != 0));
+          mma_bf16_ss_lo(d, a_lo, b_lo, idesc, (uint32_t)(c != 0));
+          mma_bf16_ss_lo(d, a_lo + 2, b_lo + 2, idesc, 1u);
+          mma_bf16_ss_lo(d, a_lo + 4, b_lo + 4, idesc, 1u);
+          mma_bf16_ss_lo(d, a_lo + 6, b_lo + 6, idesc, 1u);
 #endif
-          mma_commit(&bars->b_empty[s]);
-          if (c == kp.KC - 1)
-            for (int nb = nb0; nb < nb1; ++nb) mma_commit(&bars->acc_full[nb]);
+          commit_s(b_empty0 + bs * 8);
+          if (last_slice) commit_s(acc_full0 + nb * 8);
+          if (nb == NB - 1) commit_s(a_empty0 + ab * 8);
         }
         __syncwarp();
+        if (++bs == B_STAGES) { bs = 0; b_par ^= 1; }
       }
-      if (elect_one()) mma_commit(&bars->a_empty[ab]);
-      __syncwarp();
-      TR(0, it * 4 + 1);
+      if (++ab == A_BUFS) { ab = 0; a_par ^= 1; }
     }
+    if (!first_tile) acc_par ^= 1;
+    first_tile = false;
   }
-#ifdef CP_PROFILE_PHASES
-  for (int i = 8; i < 11; ++i) atomicAdd(&cp_dbg_phase[i], (unsigned long long)ph[i]);
-#endif
 }
 
 // Ring position of the next round (U rows, contiguous): a pure function of the list lengths of the tiles this CTA

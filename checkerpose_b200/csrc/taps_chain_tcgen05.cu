@@ -195,15 +195,17 @@ __device__ void mma_issuer(const TcParams& kp, uint8_t* sm, Bars* bars, uint32_t
   uint32_t st = 0;      // accumulator stages issued (slot = st & 1)
   uint32_t hcnt = 0;    // h_full phases consumed
   const uint32_t idesc = make_idesc_bf16_m128(128);
+  const uint32_t b_lo0 = smem_desc_lo(smem_u32(sm + OFF_B));
   auto gemm_block = [&](uint32_t a_addr, uint32_t d, bool accumulate) {   // one 128 x 128 x 64 block against the next weight tile
     const int s = wcnt % B_STAGES;
     mbar_wait(&bars->b_full[s], (wcnt / B_STAGES) & 1);
     tc_fence_after_sync();
-    const uint32_t b_addr = smem_u32(sm + OFF_B + s * B_STAGE_BYTES);
+    const uint32_t a_lo = smem_desc_lo(a_addr), b_lo = b_lo0 + s * (B_STAGE_BYTES >> 4);
     if (elect_one()) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        mma_bf16_ss(d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc, (uint32_t)(accumulate || k != 0));
+      mma_bf16_ss_lo(d, a_lo, b_lo, idesc, (uint32_t)accumulate);
+      mma_bf16_ss_lo(d, a_lo + 2, b_lo + 2, idesc, 1u);
+      mma_bf16_ss_lo(d, a_lo + 4, b_lo + 4, idesc, 1u);
+      mma_bf16_ss_lo(d, a_lo + 6, b_lo + 6, idesc, 1u);
       mma_commit(&bars->b_empty[s]);
     }
     __syncwarp();

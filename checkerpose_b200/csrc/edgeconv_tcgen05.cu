@@ -705,10 +705,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
   const uint32_t tmem_base = bars->tmem_slot;
 
   if (warp >= STG_WARP0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_STG));
+    if (REGS_STG < 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_STG));
     stager<KCH>(kp, sm, bars, warp - STG_WARP0, lane);
   } else if (warp >= W_WARP) {   // control warpgroup
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+    if (REGS_CTRL < 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
     if (warp == MMA_WARP) {
       mma_issuer(kp, sm, bars, tmem_base);
     } else if (warp == W_WARP) {
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edgeconv_kernel(const __grid_cons
       else epilogue_warps<false, false>(kp, &out_map, sm, bars, tmem_base, q, lane);
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_AGG));
+    if (REGS_AGG > 64) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_AGG));
     aggregator<KCH>(kp, sm, bars, warp, lane);
   }
 

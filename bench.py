@@ -233,6 +233,15 @@ def run_ours(args):
                 "traffic_source": DOMINANT_KERNEL_DRAM_SOURCE,
                 "avg_launch_ms": avg_ms, "launches_per_step": len(dom) / args.steps, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": sum(dom) / ms_total if world == 1 else None, "all_gnn_kernels_share_of_step": allchain / ms_total if world == 1 else None}
+        # the resource that actually binds this kernel: the SM's 128 B/clk shared-memory port.
+        # Bytes that cross it per 128-node tile at C = C' = 256 (row reads 865 KB, weights 256 + 256, A operand 64 + 256,
+        # epilogue tiles 128 + 128, staging 125, programs / bias 30), against the measured launch time at the maximum SM clock
+        smem_tile_bytes = 2.1e6
+        tiles_per_sm = B * (N // 128) / 148.0
+        smem_min_ms = tiles_per_sm * (smem_tile_bytes / 128.0) / (1965.0e6) * 1e3
+        roof["onchip"] = {"bound": "shared-memory port (128 B/clk/SM)", "bytes_per_tile": smem_tile_bytes,
+                          "min_launch_ms_at_1965MHz": smem_min_ms, "frac": smem_min_ms / avg_ms,
+                          "note": "informational: roofline.frac above is against the HBM bound north_star names"}
 
     # second kernel of north_star's list: K3, 4-tap sampling + pre-graph MLP + first [P|Q] GEMM (stages 1, 2: Cg = 256)
     k3 = [a.elapsed_time(b) for sig, a, b in log if sig[0] == ops.PRO_TAPS and sig[1] == 512]

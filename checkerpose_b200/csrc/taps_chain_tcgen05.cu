@@ -33,9 +33,13 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_G_WARPS = 4, G_THREADS = NUM_G_WARPS * 32;
-constexpr int E_WARP0 = 4, NUM_E_WARPS = 8;
-constexpr int W_WARP = 12, MMA_WARP = 13;
-constexpr int NUM_WARPS = 16;   // two idle warps: 512 threads leave 128 registers per thread
+#ifndef CP_K3_EWARPS
+#define CP_K3_EWARPS 8
+#endif
+constexpr int E_WARP0 = 4, NUM_E_WARPS = CP_K3_EWARPS;      // a multiple of 4: NUM_E_WARPS / 4 warps per TMEM lane quarter
+constexpr int W_WARP = E_WARP0 + NUM_E_WARPS, MMA_WARP = W_WARP + 1;
+constexpr int NUM_WARPS = NUM_E_WARPS == 8 ? 16 : MMA_WARP + 1;   // 8 epilogue warps: two idle warps, 512 threads leave 128 registers per thread
+static_assert(NUM_E_WARPS % 4 == 0 && E_WARP0 % 4 == 0, "epilogue warp w drains TMEM lane quarter w % 4");
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int CHUNK_BYTES = TILE_M * 128;   // 128 rows x 64 bf16
 #ifndef CP_K3_NX
@@ -314,7 +318,7 @@ __device__ void epilogue_warps(const TcParams& kp, const CUtensorMap* out_map, u
         ++hfree;
       }
       const uint32_t tbase = tmem_base + slot * ACC_COLS + ((uint32_t)(q * 32) << 16);
-      for (int c0 = hh * 32; c0 < ncols; c0 += 64) {
+      for (int c0 = hh * 32; c0 < ncols; c0 += 32 * (NUM_E_WARPS / 4)) {
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) taps_chain_kernel(const __grid_co
       mbar_init(&bars->b_full[s], 1);
       mbar_init(&bars->b_empty[s], 1);
     }
-    for (int c = 0; c < NH; ++c) mbar_init(&bars->h_full[c], NUM_E_WARPS);   // the 8 warps: 4 lane quarters x 2 column halves of the chunk
+    for (int c = 0; c < NH; ++c) mbar_init(&bars->h_full[c], 8);   // 4 lane quarters x the 2 32-column blocks of the chunk
     mbar_init(&bars->h_free, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->acc_full[s], 1);

@@ -260,6 +260,14 @@ int cp_id_to_bits(const int64_t* ids, int64_t count, int L, int base, float* out
  * out[g*inner + i] = argmax_d x[g, d, i] (first maximum wins, like numpy.argmax) as int64. */
 int cp_group_argmax(const float* x, int64_t G, int D, int64_t inner, int64_t* out, cp_stream_t s);
 
+/* ---- offline keypoint preparation ---------------------------------
+ * farthest_point_sample_init_center(xyz, npoint)  preprocess_data/get_fps_points.py:65-90, float64, the reference's
+ * operation order (bit-exact ids).  xyz (V,3) f64 vertices; center (3) f64 HOST values = (max + min) / 2 and
+ * init_dist = 10 * |max - min| (computed by the caller as the reference does, :74-80); dist_ws (V) f64 workspace;
+ * ids (npoint) int64 and fps_xyz (npoint,3) f64 outputs.  One CTA; O(npoint * V). */
+int cp_fps(const double* xyz, int V, int npoint, const double* center, double init_dist, double* dist_ws,
+           int64_t* ids, double* fps_xyz, cp_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

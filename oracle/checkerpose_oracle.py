@@ -264,6 +264,28 @@ def pose_head_abwoprog(img_feats, sd, init_knn_idx, refine_knn_idx, npoint, res_
     return roi_bit, x_bits, y_bits, seg, from_code_prob_to_id(x_bits), from_code_prob_to_id(y_bits)
 
 
+def farthest_point_sample_init_center(xyz, npoint):
+    """preprocess_data/get_fps_points.py:65-90, restated line by line (NumPy float64)."""
+    xyz = np.asarray(xyz, dtype=np.float64)
+    num_xyz = xyz.shape[0]
+    xyz_max = xyz.max(axis=0)
+    xyz_min = xyz.min(axis=0)
+    farthest_xyz = (xyz_max + xyz_min) / 2
+    xyz_extent = np.linalg.norm(xyz_max - xyz_min)
+    fps_xyz = np.zeros((npoint, 3))
+    fps_ids = []
+    distances_to_set = np.ones(num_xyz) * xyz_extent * 10
+    for sample_id in range(npoint):
+        distances = np.linalg.norm((xyz - farthest_xyz), axis=1)
+        mask = distances < distances_to_set
+        distances_to_set[mask] = distances[mask]
+        farthest_id = int(np.argmax(distances_to_set))
+        farthest_xyz = xyz[farthest_id, :]
+        fps_ids.append(farthest_id)
+        fps_xyz[sample_id, :] = farthest_xyz
+    return fps_ids, fps_xyz
+
+
 def roi_xy_ori(bbox, size):
     """bbox (4,) [x,y,w,h] -> (size,size,2) grid: (x + u*w/size, y + v*h/size)."""
     bbox = np.asarray(bbox, dtype=np.float64)

@@ -325,6 +325,33 @@ def golden_heads():
              checksum_feat=np.array([syn.tensor_checksum(f) for f in feats]).sum())
 
 
+def fps_case_cloud(case):
+    """Synthetic CAD-like vertex clouds (float64, mm), regenerated from the seed by the tests (must mirror tests/helpers.py)."""
+    g = torch.Generator().manual_seed(7000 + case)
+    V = (3000, 1531, 20000)[case]
+    d = torch.randn(V, 3, generator=g, dtype=torch.float64)
+    d = d / d.norm(dim=1, keepdim=True)
+    r = 40.0 + 15.0 * torch.sin(3.0 * d[:, 0]) * torch.cos(2.0 * d[:, 1]) + torch.rand(V, generator=g, dtype=torch.float64)
+    xyz = d * r[:, None] * torch.tensor([1.0, 0.6, 1.4], dtype=torch.float64)
+    if case == 1:     # duplicated vertices: argmax ties resolve to the first index
+        xyz = torch.cat([xyz, xyz[:300]], dim=0)
+    return xyz.numpy()
+
+
+def golden_fps():
+    """farthest_point_sample_init_center of the unmodified reference (preprocess_data/get_fps_points.py:65-90)."""
+    sys.path.insert(0, os.path.join(REF, "preprocess_data"))
+    import get_fps_points as ref_fps
+    out = {}
+    for case, npoint in ((0, 256), (1, 128), (2, 512)):
+        xyz = fps_case_cloud(case)
+        ids, fxyz = ref_fps.farthest_point_sample_init_center(xyz, npoint)
+        out[f"c{case}_ids"] = np.asarray(ids, dtype=np.int64)
+        out[f"c{case}_xyz"] = fxyz
+        out[f"c{case}_checksum"] = np.float64(syn.tensor_checksum(torch.from_numpy(xyz)))
+    save("fps", **out)
+
+
 ABWOPROG_CASE = ("lm", tuple(range(1, 16)), 128, 3, 1234 + 7)   # must mirror tests/helpers.py::ABWOPROG_CASE
 
 
@@ -357,9 +384,11 @@ def golden_abwoprog():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["knn", "modules", "decode", "corr", "heads", "abwoprog"]
+    which = sys.argv[1:] or ["knn", "modules", "decode", "corr", "heads", "abwoprog", "fps"]
     if "abwoprog" in which:
         golden_abwoprog()
+    if "fps" in which:
+        golden_fps()
     if "knn" in which:
         golden_knn()
     if "modules" in which:

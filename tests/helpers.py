@@ -29,6 +29,22 @@ def head_case_inputs(name):
     return p3d, sd, feats, obj_ids
 
 
+def fps_case_cloud(case):
+    """must mirror tests/golden/make_golden.py::fps_case_cloud"""
+    g = torch.Generator().manual_seed(7000 + case)
+    V = (3000, 1531, 20000)[case]
+    d = torch.randn(V, 3, generator=g, dtype=torch.float64)
+    d = d / d.norm(dim=1, keepdim=True)
+    r = 40.0 + 15.0 * torch.sin(3.0 * d[:, 0]) * torch.cos(2.0 * d[:, 1]) + torch.rand(V, generator=g, dtype=torch.float64)
+    xyz = d * r[:, None] * torch.tensor([1.0, 0.6, 1.4], dtype=torch.float64)
+    if case == 1:     # duplicated vertices: argmax ties resolve to the first index
+        xyz = torch.cat([xyz, xyz[:300]], dim=0)
+    return xyz.numpy()
+
+
+FPS_CASES = ((0, 256), (1, 128), (2, 512))
+
+
 # must mirror tests/golden/make_golden.py::ABWOPROG_CASE
 ABWOPROG_CASE = ("lm", tuple(range(1, 16)), 128, 3, 1234 + 7)
 

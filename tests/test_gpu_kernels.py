@@ -483,3 +483,16 @@ def test_bias_add_rows(cp, relu):
         ref = ref.clamp_min(0)
     got = ops.bias_add_rows_(x.cuda().to(torch.bfloat16), bias.cuda(), relu)
     assert torch.equal(got.cpu().float(), _bf16_round(ref))
+
+
+def test_fps_bit_exact(cp, golden):
+    """cp_fps through the drop-in farthest_point_sample_init_center: ids and points bit-exact with the reference's float64
+    NumPy loop (get_fps_points.py:65-90), duplicate vertices (argmax ties) included."""
+    from helpers import FPS_CASES, fps_case_cloud
+    from checkerpose_b200.preprocess_data.get_fps_points import farthest_point_sample_init_center
+    g = golden("fps")
+    for case, npoint in FPS_CASES:
+        ids, fxyz = farthest_point_sample_init_center(fps_case_cloud(case), npoint)
+        assert isinstance(ids, list) and fxyz.shape == (npoint, 3) and fxyz.dtype == np.float64
+        assert np.array_equal(np.asarray(ids), g[f"c{case}_ids"])
+        assert np.array_equal(fxyz, g[f"c{case}_xyz"])

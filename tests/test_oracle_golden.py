@@ -135,3 +135,14 @@ def test_abwoprog_head(golden):
     for a, k in ((roi, "roi_bit"), (xb, "x_bits"), (yb, "y_bits"), (seg, "seg")):
         assert torch.allclose(a, torch.from_numpy(g[k]), rtol=1e-4, atol=1e-4), k
     assert xb.shape == (B, 6, N) and yb.shape == (B, 6, N) and xid.dtype == torch.int64
+
+
+def test_fps(golden):
+    """oracle.farthest_point_sample_init_center vs the unmodified reference (get_fps_points.py:65-90)."""
+    from helpers import FPS_CASES, fps_case_cloud, syn
+    g = golden("fps")
+    for case, npoint in FPS_CASES:
+        xyz = fps_case_cloud(case)
+        assert np.isclose(syn.tensor_checksum(torch.from_numpy(xyz)), float(g[f"c{case}_checksum"]), rtol=1e-12)
+        ids, fxyz = orc.farthest_point_sample_init_center(xyz, npoint)
+        assert np.array_equal(np.asarray(ids), g[f"c{case}_ids"]) and np.array_equal(fxyz, g[f"c{case}_xyz"])

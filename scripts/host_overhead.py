@@ -8,6 +8,8 @@ from checkerpose_b200.model import init, pipeline
 from checkerpose_b200.model.backbone import FeatureListBackbone
 
 torch.set_grad_enabled(False)
+if os.environ.get("CUDNN_BENCHMARK"):
+    torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda", 0)
 B, N = int(os.environ.get("KB_B", 256)), 4096
 head.set_compute_dtype(torch.bfloat16)

@@ -272,7 +272,9 @@ def run_ours(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     h2d_bytes = sum(f.numel() * f.element_size() for f in feats)
-    host_corr = torch.empty((B * world if world > 1 else B, N, 3), dtype=torch.int32).pin_memory()
+    # rank 0 reads back ALL gathered records (it is the consumer of the gather); the other ranks read back their own shard
+    d2h_rows = B * world if rank == 0 else B
+    host_corr = torch.empty((d2h_rows, N, 3), dtype=torch.int32).pin_memory()
     d2h_bytes = host_corr.numel() * 4
 
     def upload(i):
@@ -304,7 +306,8 @@ def run_ours(args):
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(produced)
                 corr.record_stream(d2h_stream)
-                host_corr2[i % 2].copy_(corr, non_blocking=True)
+                src = corr if (world == 1 or rank == 0) else corr[rank * B:(rank + 1) * B]
+                host_corr2[i % 2].copy_(src, non_blocking=True)
                 d2h_done[i % 2].record(d2h_stream)
         main.synchronize()
         d2h_stream.synchronize()                    # every step's records are on the host when the timed region ends
@@ -345,7 +348,8 @@ def run_ours(args):
                        "collective": "all_gather_into_tensor of correspondence records per step" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "note": "pinned host feature maps -> PoseNet_GNNskip.forward_with_correspondences -> pinned host records; "
-                            "next step's H2D and the previous step's D2H overlap compute on copy streams"},
+                            "next step's H2D and the previous step's D2H overlap compute on copy streams; with N > 1 rank 0 reads back all "
+                            "gathered records (d2h_bytes_per_step), the other ranks their own shard"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_k3": roof_k3, "cpu_baseline": cpu_base,
         }))
     if world > 1:

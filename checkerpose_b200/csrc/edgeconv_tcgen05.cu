@@ -566,10 +566,12 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
     const bool row_ok = row < rows_valid;
     const size_t grow0 = (size_t)b * p.N + n0;
     PH_T(e0);
-    PH_T(e1);
     for (int c0 = h * 32; c0 < kp.NB * 128; c0 += 32 * (NUM_EPI_WARPS / 4)) {
       if ((c0 & 127) == h * 32) {   // this warp's first block of a 128-column accumulator block
+        PH_T(w0);
         mbar_wait_idle(&bars->acc_full[c0 >> 7], ti & 1);
+        PH_T(w1);
+        PH_ADD(6, w0, w1);
         tc_fence_after_sync();
       }
       if (lane == 0 && (ew == 0 || ew == 7)) TR(3 + (ew == 7), ti * 8 + (c0 >> 6));
@@ -653,7 +655,7 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
       }
     }
 #ifdef CP_PROFILE_PHASES
-    { PH_T(e2); PH_ADD(6, e0, e1); PH_ADD(7, e1, e2); }
+    { PH_T(e2); PH_ADD(7, e0, e2); }   // [6] = waiting for accumulator blocks, [7] = the whole tile (waits included)
 #endif
   }
 #ifdef CP_PROFILE_PHASES

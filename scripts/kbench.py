@@ -59,8 +59,7 @@ def main():
             rounds = tiles * 4 * 16
             names = ["-", "-", "stg_full wait", "Q+reduce", "a_empty wait", "finish+store+arrive"]
             print("   aggregator, clk per warp-round: " + ", ".join(f"{n} {buf[i] / rounds:.0f}" for i, n in enumerate(names) if n != "-"))
-            print(f"   epilogue, clk per warp-tile: acc_full wait {buf[6] / tiles / 8:.0f}, drain {buf[7] / tiles / 8:.0f};  "
-                  f"MMA thread, clk per tile: acc_empty wait {buf[8] / tiles:.0f}, a_full wait {buf[9] / tiles:.0f}, b_full wait {buf[10] / tiles:.0f}")
+            print(f"   epilogue, clk per warp-tile: waiting for accumulator blocks {buf[6] / tiles / 8:.0f}, tile total {buf[7] / tiles / 8:.0f}")
         if hasattr(lib, "cp_debug_read_trace"):       # CP_TRACE builds: timeline of CTA 0, tiles 8..11
             import ctypes
             buf = (ctypes.c_longlong * 8192)()
@@ -73,15 +72,9 @@ def main():
                     it = ti * 4 + c
                     a0 = [tr[1][it * 4 + k] - t0 for k in range(4)]
                     a15 = [tr[2][it * 4 + k] - t0 for k in range(4)]
-                    m = [tr[0][it * 4 + k] - t0 for k in range(2)]
                     st = [tr[5][it * 2 + k] - t0 for k in range(2)]
                     print(f"     round {it}: agg0 start {a0[0]:7d} stg_ok {a0[1]:7d} reduced {a0[2]:7d} a_empty_ok {a0[3]:7d} | agg15 {a15[0]:7d} {a15[1]:7d} {a15[2]:7d} {a15[3]:7d}"
-                          f" | mma a_full_ok {m[0]:7d} issued {m[1]:7d} | stager space_ok {st[0]:7d} issued {st[1]:7d}")
-                for c in range(4):
-                    it = ti * 4 + c
-                    if (it * 4 + 3) * 3 + 2 < 1024:
-                        print(f"     mma round {it}: " + " | ".join(
-                            "b_full_ok {:7d} mma_issued {:7d} committed {:7d}".format(*[tr[6][(it * 4 + nb) * 3 + k] - t0 for k in range(3)]) for nb in range(4)))
+                          f" | stager space_ok {st[0]:7d} issued {st[1]:7d}")
                 e0 = [tr[3][ti * 8 + k] - t0 for k in range(8)]
                 e7 = [tr[4][ti * 8 + k] - t0 for k in range(8)]
                 print(f"     epilogue warp0 blocks (cols 0,64,..): {e0[0::1]}")

@@ -108,6 +108,31 @@ def test_state_dict_layout_matches_reference_keys():
     assert want == {k: tuple(v.shape) for k, v in bare.state_dict().items()}
 
 
+def test_abwoprog_state_dict_layout_and_reference_import_surface():
+    """pipeline_lm exports what test_lm.py:27 / train_lm.py:23 import, and the ablation net's state_dict layout is the one
+    the unmodified reference module loaded in tests/golden/make_golden.py::golden_abwoprog."""
+    from checkerpose_b200.model import init_lm, pipeline_lm
+    from checkerpose_b200.model.backbone import FeatureListBackbone
+    from checkerpose_b200.model.pipeline_lm import PoseNet_GNNskip, PoseNet_GNNskip_ABwoProg  # noqa: F401  (the reference's import line)
+    N = 64
+    p3d = torch.cat([syn.p3d_normed_tensor(syn.load_fps_xyz("lm", o, N)) for o in (1, 2)], dim=0)
+    inet = init_lm.InitNet_GNN(npoint=N, p3d_normed=p3d, res_log2=3, backbone_name="hrnet_w18", pretrain_backbone=False,
+                               img_backbone=FeatureListBackbone())
+    net = pipeline_lm.PoseNet_GNNskip_ABwoProg(inet, npoint=N, p3d_normed=p3d, res_log2=6, local_k=2, num_graph_module=3)
+    want = {k: tuple(s) for k, s, _, _ in syn.abwoprog_param_spec(N)}
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert want == got
+    assert got["query_block.mlps.4.weight"] == (13, 64)      # one query for all 2 * res_log2 + 1 bits
+
+
+def test_fps_dropin_needs_gpu():
+    from checkerpose_b200.preprocess_data.get_fps_points import farthest_point_sample_init_center
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError):
+        farthest_point_sample_init_center(np.zeros((10, 3)), 4)
+
+
 def test_synthetic_generators_are_deterministic():
     a = syn.synthetic_state_dict(syn.head_param_spec(64), torch.Generator().manual_seed(5))
     b = syn.synthetic_state_dict(syn.head_param_spec(64), torch.Generator().manual_seed(5))

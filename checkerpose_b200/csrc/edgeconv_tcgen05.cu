@@ -72,7 +72,8 @@ constexpr int A_BUF_BYTES = TILE_M * 128;    // one K slice of the A operand: 12
 #endif
 constexpr int A_BUFS = CP_A_BUFS;
 #ifndef CP_MMA_N
-#define CP_MMA_N 128                         // columns per tcgen05.mma (128 or 256): 256 halves the A-operand re-reads
+#define CP_MMA_N 128                         // columns per tcgen05.mma.  256 (32 KB stages, half the A re-reads) was measured no
+                                             // faster with the earlier issue loop; the current mma_issuer is N = 128 only
 #endif
 constexpr int MMA_N = CP_MMA_N;
 constexpr int B_STAGE_BYTES = MMA_N * 128;   // one K slice of MMA_N weight rows

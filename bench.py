@@ -148,6 +148,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU port"
     torch.cuda.set_device(local)
+    numa_bound = cpdist.bind_to_gpu_numa_node(local) if world > 1 else False   # before any pinned allocation
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -349,7 +350,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "note": "pinned host feature maps -> PoseNet_GNNskip.forward_with_correspondences -> pinned host records; "
                             "next step's H2D and the previous step's D2H overlap compute on copy streams; with N > 1 rank 0 reads back all "
-                            "gathered records (d2h_bytes_per_step), the other ranks their own shard"},
+                            "gathered records (d2h_bytes_per_step), the other ranks their own shard",
+                    "numa_bound": numa_bound},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_k3": roof_k3, "cpu_baseline": cpu_base,
         }))
     if world > 1:

@@ -8,6 +8,29 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Best effort: pin the calling process to the CPUs NVML lists as local to GPU ``device_index``, so that the pinned
+    host buffers it allocates afterwards (first touch) live on that GPU's NUMA node.  With one process per GPU on a
+    two-socket box the host->device uploads of the end-to-end path otherwise cross the socket interconnect.  Returns
+    False (and changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        # honour CUDA_VISIBLE_DEVICES: map the torch index to the physical one when it is a plain index list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
+
+
 def shard_range(total: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of ``total`` RoIs for ``rank``; sizes differ by at most one."""
     base, rem = divmod(total, world)

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) chain_kernel(const __grid_constan
   sm.acc = sm.empty + STAGES;
   sm.tmem_slot = reinterpret_cast<uint32_t*>(sm.acc + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&sm.full[s], 1);

@@ -38,7 +38,6 @@ namespace {
 
 constexpr int TILE_M = CP_PLAN_TILE;
 constexpr int NUM_AGG_WARPS = 16;            // 64 quarter-warps = the 64 node pairs of a tile
-constexpr int AGG_THREADS = NUM_AGG_WARPS * 32;
 constexpr int NUM_QW = NUM_AGG_WARPS * 4;
 constexpr int EPI_WARP0 = NUM_AGG_WARPS;                 // TMEM lane quarter = warp % 4; NUM_EPI_WARPS / 4 warps share a quarter's columns
 constexpr int NUM_EPI_WARPS = 8;
@@ -191,8 +190,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint32_t a_offset(int buf, int row, int chunk) {
   return (uint32_t)(OFF_A + buf * A_BUF_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4));

@@ -53,6 +53,7 @@ SIGNATURES = {
     "cp_last_error_string": (C.c_char_p, []),
     "cp_version": (c_i32, []),
     "cp_device_arch": (c_i32, []),
+    "cp_graph_sel": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "cp_knn": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp_transpose_cn_to_nc": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "cp_transpose_nc_to_cn": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

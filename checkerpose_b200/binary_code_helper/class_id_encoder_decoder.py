@@ -17,6 +17,13 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def RGB_image_to_class_id_image(RGB_image):
+    """(H,W,3) integer image in OpenCV's B,G,R channel order -> (H,W) int ids = B << 16 | G << 8 | R (reference :6-15).
+    Host-side dataset helper on numpy arrays (the reference requires numpy here too); no kernel involved."""
+    img = np.asarray(RGB_image).astype(int)
+    return (img[:, :, 0] << 16) + (img[:, :, 1] << 8) + img[:, :, 2]
+
+
 def class_code_images_to_class_id_image(class_code_images, class_base=2):
     """(H,W,C) numpy code images -> (H,W) float64 ids (reference :17-28)."""
     t = torch.as_tensor(np.ascontiguousarray(class_code_images), dtype=torch.float32, device=_dev())

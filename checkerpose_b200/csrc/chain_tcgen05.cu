@@ -179,6 +179,7 @@ __device__ __forceinline__ void fill_taps(uint8_t* A, const cp_chain_params& p, 
       const float mk = p.mask ? __ldg(p.mask + e) : 1.f;
       const int yy = (int)(2 * __ldg(p.y_id + e)) + ((tap & 1) ? p.tap_step : 0);
       const int xx = (int)(2 * __ldg(p.x_id + e)) + ((tap & 2) ? p.tap_step : 0);
+      if (yy < 0 || xx < 0 || yy >= p.Hp || xx >= p.Wp) __trap();   // caller error (the reference raises an index assert)
       if (mk != 0.f) off[u] = (yy * p.Wp + xx) * 64 + chunk * 8;
     }
   }
@@ -496,13 +497,7 @@ extern "C" int cp_chain_fwd(const cp_chain_params* pp, cp_stream_t s) {
   else
     CP_REQUIRE(p.out_mode == CP_OUT_F32 && p.n_valid >= 1 && p.n_valid <= p.ld_out, CP_E_INVALID, "cp_chain_fwd: bad f32 output spec");
 
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = cp::num_sms();
   int grid = kp.num_node_tiles < 2 * num_sms ? kp.num_node_tiles : 2 * num_sms;
   cudaStream_t st = (cudaStream_t)s;
   cudaError_t e = cudaSuccess;

@@ -36,6 +36,9 @@ void set_error(const char* fmt, ...);
 // clipped instead of landing in the next RoI.  map128 points at 128 bytes (a CUtensorMap).  CP_OK or an error code.
 int make_out_tensor_map(void* map128, void* out, int ncols, int ld_out, int N, int B, const char* who);
 
+// SM count of the CURRENT device (cached per device index; the persistent kernels size their grids with it)
+int num_sms();
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }

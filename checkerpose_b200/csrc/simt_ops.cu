@@ -323,6 +323,9 @@ sample_taps_kernel(const T* __restrict__ patches, int Hp, int Wp, int E, int ste
     // tap order of pipeline.py:158-162: (2y,2x), (2y+k,2x), (2y,2x+k), (2y+k,2x+k)
     const int yy = (int)(2 * yi) + ((t & 1) ? step : 0);
     const int xx = (int)(2 * xi) + ((t & 2) ? step : 0);
+    // an id outside the patch map is a caller error: the reference's advanced indexing raises a device-side index
+    // assert for it (pipeline.py:158-161); so does this kernel, instead of reading out of bounds
+    if (yi < 0 || xi < 0 || yy >= Hp || xx >= Wp) __trap();
     const T* src = pb + ((size_t)yy * Wp + xx) * E;
     for (int e = lane; e < E; e += 32) ob[t * E + e] = cp::from_f32<T>(cp::to_f32<T>(src[e]) * mk);
   }
@@ -493,8 +496,25 @@ inline int grid_for(int64_t n, int block = 256) {
 
 }  // namespace
 
+// 1-based object ids -> 0-based graph selector (pipeline_lm.py:56-57: self.knn_idx[obj_ids-1]); an id outside [1, G]
+// traps, like the reference's device-side index assert
+__global__ void graph_sel_kernel(const int64_t* __restrict__ obj_ids, int64_t n, int G, int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t g = obj_ids[i] - 1;
+  if (g < 0 || g >= G) __trap();
+  out[i] = (int32_t)g;
+}
+
 // ================================================================================================
 extern "C" {
+
+int cp_graph_sel(const int64_t* obj_ids, int64_t n, int G, int32_t* out, cp_stream_t s) {
+  CP_REQUIRE(obj_ids && out && n > 0 && G > 0, CP_E_INVALID, "cp_graph_sel: bad arguments");
+  graph_sel_kernel<<<cp::ceil_div(n, 256), 256, 0, (cudaStream_t)s>>>(obj_ids, n, G, out);
+  CP_CHECK_LAUNCH("cp_graph_sel");
+  return CP_OK;
+}
 
 int cp_transpose_cn_to_nc(const void* src, int sd, void* dst, int dd, int B, int C, int N, cp_stream_t s) {
   CP_REQUIRE(src && dst && B > 0 && C > 0 && N > 0, CP_E_INVALID, "cp_transpose_cn_to_nc: bad arguments");

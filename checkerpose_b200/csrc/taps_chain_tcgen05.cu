@@ -134,6 +134,8 @@ __device__ void gather_warps(const TcParams& kp, uint8_t* sm, Bars* bars, int gw
         const size_t e = (size_t)b * p.N + n0 + r;
         const float mk = p.mask ? __ldg(p.mask + e) : 1.f;
         const int yy = (int)(2 * __ldg(p.y_id + e)), xx = (int)(2 * __ldg(p.x_id + e));
+        // caller error (the reference raises a device-side index assert, pipeline.py:158-161): never read out of bounds
+        if (yy < 0 || xx < 0 || yy + p.tap_step >= p.Hp || xx + p.tap_step >= p.Wp) __trap();
         if (mk != 0.f) o[i] = (yy * p.Wp + xx) * 128;
       }
     }
@@ -459,13 +461,7 @@ bool taps_chain_try(const cp_chain_params& p, cudaStream_t s, int* rc) {
     for (int c = 0; c < NH; ++c)
       for (int nb = 0; nb < kp.P2; ++nb) kp.wt[T++] = {tile_ptr(L2, half * 2 + nb, c), 128 * 128, 0};
   kp.T = T;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = cp::num_sms();
   const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
   cudaError_t e = cudaFuncSetAttribute(taps_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) {

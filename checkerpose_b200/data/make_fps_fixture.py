@@ -6,7 +6,7 @@ Source (read-only, this container only):
 Each pickle holds {'npoint': 4096, 'id': [...], 'xyz': (4096,3) float64 in mm}; every value is
 exactly float32-representable (checked below), so the fixture stores float32.
 
-Output: tests/golden/fps_202212.npz with one array per object, key "<dataset>/<obj_id>".
+Output: checkerpose_b200/data/fps_202212.npz with one array per object, key "<dataset>/<obj_id>".
 These are DATA fixtures (keypoint clouds), not reference source code.
 """
 import glob, os, pickle

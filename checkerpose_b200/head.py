@@ -75,10 +75,21 @@ class PreparedEdgeConv(PreparedLinear):
         super().__init__(wf, bf, want_packed)
         self.C, self.Co = wf.shape[1], wf.shape[0] // 2
         self.slope = float(act.negative_slope)
+        if self.slope < 0.0:
+            # lrelu(max_k P_j + Q_i) == max_k lrelu(P_j + Q_i) needs an increasing activation
+            raise RuntimeError("the factored EdgeConv kernels need a LeakyReLU with negative_slope >= 0 "
+                               f"(got {self.slope}): the max over neighbours must commute with the activation")
+
+
+def _ver(t: torch.Tensor) -> int:
+    """Version counter of a tensor.  Inference tensors (created under ``torch.inference_mode()``) do not track one and
+    raise when ``_version`` is read; they cannot be modified in place outside inference mode either, so a constant is a
+    valid cache key for them (a replaced tensor has another ``data_ptr`` / identity)."""
+    return -1 if t.is_inference() else t._version
 
 
 def _param_fingerprint(module: nn.Module):
-    return tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in list(module.parameters()) + list(module.buffers()))
+    return tuple((t.data_ptr(), _ver(t), t.device, t.dtype) for t in list(module.parameters()) + list(module.buffers()))
 
 
 class PrepCache:
@@ -122,8 +133,8 @@ class GraphTable:
     def get(cls, knn_idx: torch.Tensor, device) -> torch.Tensor:
         device = torch.device(device)
         hit = getattr(knn_idx, "_cp_idx32", None)
-        if hit is None or hit[0] != knn_idx._version or hit[1].device != device:
-            hit = (knn_idx._version, knn_idx.to(device=device, dtype=torch.int32).contiguous())
+        if hit is None or hit[0] != _ver(knn_idx) or hit[1].device != device:
+            hit = (_ver(knn_idx), knn_idx.to(device=device, dtype=torch.int32).contiguous())
             knn_idx._cp_idx32 = hit
         return hit[1]
 
@@ -141,7 +152,9 @@ def graph_select(knn_idx, obj_ids, batch: int, device):
 
 def _graph_sel(G, obj_ids, batch, device):
     if obj_ids is not None:
-        return (obj_ids.to(device=device, dtype=torch.int64) - 1).to(torch.int32).contiguous()
+        # 1-based object ids -> 0-based graph selector; ids outside [1, G] trap on the device (the reference's
+        # ``self.knn_idx[obj_ids-1]`` raises a device-side index assert for them)
+        return ops.graph_sel(obj_ids.to(device=device), G)
     if G == 1:
         return None
     if G != batch:
@@ -172,12 +185,35 @@ def graph_ctx(knn_src, obj_ids, batch: int, device) -> GraphCtx:
     device = torch.device(device)
     t = _graph_tensor(knn_src, device)
     hit = getattr(t, "_cp_plan", None)
-    if hit is None or hit[0] != t._version or hit[1].perm.device != device:
+    if hit is None or hit[0] != _ver(t) or hit[1].perm.device != device:
         xyz = getattr(knn_src, "p3d_normed", None)
-        hit = (t._version, ops.GraphPlan(GraphTable.get(t, device), xyz))
+        hit = (_ver(t), ops.GraphPlan(GraphTable.get(t, device), xyz))
         t._cp_plan = hit
     plan = hit[1]
     return GraphCtx(plan, _graph_sel(plan.G, obj_ids, batch, device))
+
+
+def _first_cuda_device(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+        if isinstance(a, (list, tuple)):
+            for t in a:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    return t.device
+    return None
+
+
+class DeviceScopedModule(nn.Module):
+    """nn.Module whose call runs with the CUDA device of its first tensor argument current: the kernels launch on the
+    current device's current stream (ops._need_cuda), so a net moved to ``cuda:1`` works without ``torch.cuda.set_device``."""
+
+    def __call__(self, *args, **kwargs):
+        dev = _first_cuda_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return super().__call__(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return super().__call__(*args, **kwargs)
 
 
 def _require_eval(module):

@@ -18,7 +18,7 @@ CONV1X1_IN_CHANS = {
 }
 
 
-class InitNet_GNN(nn.Module):
+class InitNet_GNN(head.DeviceScopedModule):
     """init.py:71-128.  Extra keyword ``img_backbone`` (default None = timm, as the reference) lets
     synthetic runs inject ``FeatureListBackbone``; it adds no parameters."""
 

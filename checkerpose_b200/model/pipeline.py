@@ -49,7 +49,8 @@ class LazyKnnGraph:
         if stale:
             if dev is None or dev.type != "cuda":
                 raise RuntimeError("the kNN graph is built by a CUDA kernel: move the keypoints or the net to a GPU first")
-            self._idx = ops.knn(self.p3d_normed.to(dev), self.k)
+            with torch.cuda.device(dev):
+                self._idx = ops.knn(self.p3d_normed.to(dev), self.k)
         return self._idx
 
 
@@ -64,7 +65,7 @@ def _to_io(x_nm, like_dtype):
     return ops.convert(x_nm, like_dtype).permute(0, 2, 1)
 
 
-class StaticGraph_module(nn.Module):
+class StaticGraph_module(head.DeviceScopedModule):
     """EdgeConv with a fixed kNN graph (pipeline.py:45-59): kernel K2."""
 
     def __init__(self, input_dim, output_dim, knn_idx, leaky_slope=0.2):
@@ -130,7 +131,7 @@ def from_mask_prob_to_mask(mask_prob):
     return ops.threshold(mask_prob, thr=0.0, apply_sigmoid=False, as_long=False)  # pipeline.py:120-127
 
 
-class Index2Feat_module(nn.Module):
+class Index2Feat_module(head.DeviceScopedModule):
     """Patch embedding conv + exact 4-tap integer gather (pipeline.py:130-164): kernel K3."""
 
     def __init__(self, feat_dim, embed_dim=None, kernel_size=2):
@@ -147,7 +148,7 @@ class Index2Feat_module(nn.Module):
         return _to_io(out, img_feat_highres.dtype)
 
 
-class MLP_QueryNet(nn.Module):
+class MLP_QueryNet(head.DeviceScopedModule):
     """Linear stack on (B,N,C) tensors; ``pts`` is unused, as in the reference (pipeline.py:168-180)."""
 
     def __init__(self, feat_dims=(256, 256, 64), pt_dim=3, out_dim=4, leaky_slope=0.01):
@@ -191,7 +192,7 @@ def get_gdrn_upsample_module(is_convtrans=False, in_channels=512, num_filters=25
     return nn.Sequential(*layers)
 
 
-class Refine_moduleGNN(nn.Module):
+class Refine_moduleGNN(head.DeviceScopedModule):
     """One refine stage (pipeline.py:214-298): Index2Feat gather -> x roi mask -> cat graph feature ->
     MLP -> num_graph_module x EdgeConv -> MLP_QueryNet."""
 
@@ -244,7 +245,7 @@ class Refine_moduleGNN(nn.Module):
 Refine_moduleGNN._graph_module_cls = StaticGraph_module
 
 
-class PoseNet_GNNskip(nn.Module):
+class PoseNet_GNNskip(head.DeviceScopedModule):
     """Full progressive head (pipeline.py:301-384).  ``forward`` returns the reference's 6-tuple."""
 
     _refine_cls = Refine_moduleGNN
@@ -287,7 +288,8 @@ class PoseNet_GNNskip(nn.Module):
         """Extension: the reference's 6-tuple plus (B,N,3) int32 correspondence records
         {f32 u, f32 v, u32 flags} (first half of from_id_to_pose, test_network_with_test_data.py:50-66)."""
         img_feats = self.init_net.img_backbone(img)
-        return head.pose_head_forward(self, img_feats, obj_ids=obj_ids, stage=stage, bbox=bbox)
+        with torch.cuda.device(img_feats[-1].device):
+            return head.pose_head_forward(self, img_feats, obj_ids=obj_ids, stage=stage, bbox=bbox)
 
     def forward(self, img, p3d_normed, stage=None):
         img_feats = self.init_net.img_backbone(img)

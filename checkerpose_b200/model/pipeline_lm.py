@@ -33,7 +33,7 @@ class PoseNet_GNNskip(_single.PoseNet_GNNskip):
         return out
 
 
-class Refine_moduleGNN_ABwoProg(nn.Module):
+class Refine_moduleGNN_ABwoProg(head.DeviceScopedModule):
     """Ablation stage without progressive refinement (pipeline_lm.py:286-339): Linear+LeakyReLU x2 on the graph
     feature, then ``num_graph_module`` EdgeConv layers; no image sampling, no per-stage query."""
 
@@ -69,7 +69,7 @@ class Refine_moduleGNN_ABwoProg(nn.Module):
         return _to_io(feat, graph_feat.dtype)
 
 
-class PoseNet_GNNskip_ABwoProg(nn.Module):
+class PoseNet_GNNskip_ABwoProg(head.DeviceScopedModule):
     """Ablation net without progressive refinement (pipeline_lm.py:430-517): the stages refine the graph feature
     only; ONE MLP_QueryNet emits all 2*res_log2+1 logits at the end.  Same constructor, ``forward`` signature, return
     tuple and state_dict keys as the reference."""

@@ -33,10 +33,23 @@ def _stream():
 
 
 def _need_cuda(*tensors):
+    """Every tensor of a launch must be a CUDA tensor on ONE device, and that device must be the current one: the
+    kernels are launched on ``torch.cuda.current_stream()``, i.e. on the current device (wrap calls for another GPU in
+    ``with torch.cuda.device(t.device):`` -- the module-level forwards do)."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("checkerpose_b200: expected a CUDA tensor (there is no CPU fallback); got device "
                                f"{t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"checkerpose_b200: tensors of one launch live on different devices ({dev} and {t.device})")
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise RuntimeError(f"checkerpose_b200: tensors live on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "wrap the call in `with torch.cuda.device(...)`")
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -387,6 +400,17 @@ def edgeconv_fwd(*, z, plan: GraphPlan, graph_sel, agg_slope, layer, out, out_mo
         chain_event_log.append((("EC", p.Co, (layer.nout,), out_mode, p.B, p.N), e0, e1))
     else:
         check(lib.cp_edgeconv_fwd(C.byref(p), _stream()), "cp_edgeconv_fwd")
+    _count()
+    return out
+
+
+def graph_sel(obj_ids: torch.Tensor, G: int) -> torch.Tensor:
+    """1-based object ids (B) int64 -> graph selector (B) int32 = obj_ids - 1 (pipeline_lm.py:56-57); ids outside [1, G]
+    trap on the device (cp_graph_sel)."""
+    _need_cuda(obj_ids)
+    ids = obj_ids.contiguous().to(torch.int64)
+    out = torch.empty(ids.shape, dtype=torch.int32, device=ids.device)
+    check(lib.cp_graph_sel(_p(ids), ids.numel(), int(G), _p(out), _stream()), "cp_graph_sel")
     _count()
     return out
 

@@ -6,7 +6,8 @@ from a seed, on the CPU, with plain torch RNG calls (identical in this container
 box because both run the same image):
 
 * keypoint clouds: the reference's own shipped FPS files, packed once into
-  ``tests/golden/fps_202212.npz`` by ``tests/golden/make_fps_fixture.py``
+  ``checkerpose_b200/data/fps_202212.npz`` by ``checkerpose_b200/data/make_fps_fixture.py`` (input data of the
+  path, not test infrastructure: nothing under ``checkerpose_b200/`` reads ``tests/``)
   (reference loader: ``checkerpose/test.py:145-148``);
 * ``pc_normalize``: ``checkerpose/aux_utils/pointnet2_utils.py:11-20``;
 * HRNet-W18 shaped feature maps (channel table ``checkerpose/model/pipeline.py:12``);
@@ -27,7 +28,7 @@ import numpy as np
 import torch
 
 _REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FPS_FIXTURE = os.path.join(_REPO_ROOT, "tests", "golden", "fps_202212.npz")
+FPS_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "fps_202212.npz")
 
 HRNET_W18_DIMS = (128, 256, 512, 1024)   # checkerpose/model/pipeline.py:12
 HRNET_W18_SIZES = (64, 32, 16, 8)        # for a 256x256 RoI crop

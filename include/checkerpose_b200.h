@@ -182,12 +182,12 @@ typedef struct { /* DEVICE pointers to the arrays cp_graph_plan_build produced *
 /* StaticGraph_module (pipeline.py:45-59) in the factored form, fused with the GEMM that consumes it:
  *   A[i,:]  = lrelu(max_k z[b, nbr(i,k), :Co] + z[b, i, Co:2Co])       (never leaves the SM)
  *   out     = act(A . W^T + bias)                                       (tcgen05, fp32 accumulate in TMEM)
- * One persistent CTA per SM.  Per tile of 128 nodes and 64-channel slice the sixteen aggregator warps copy the
- * tile's distinct neighbour row slices (128 B each) into a shared-memory ring with cp.async, up to two slices
- * ahead of the one they reduce; a quarter-warp takes the max for one node pair in registers with 128-bit
- * shared-memory loads and writes the bf16 A operand; one thread issues the MMAs against weights streamed
- * through the TMA engine by another, and four warps drain TMEM into TMA tensor stores -- all overlapped
- * through mbarriers.
+ * One persistent CTA of 32 warps per SM (csrc/edgeconv_tcgen05.cu).  Per tile of 128 nodes and 64-channel slice a
+ * stager warpgroup copies the tile's DISTINCT neighbour row slices (128 B each, plan.ulist) into a shared-memory ring
+ * with cp.async and signals the slice asynchronously (cp.async.mbarrier.arrive.noinc); sixteen aggregator warps -- a
+ * quarter-warp per node pair of plan.prog -- take the max in registers with 128-bit shared-memory loads and write
+ * the bf16 A operand; one thread issues the MMAs against weights streamed through the TMA engine by another, and
+ * eight epilogue warps drain TMEM into TMA tensor stores -- all overlapped through mbarriers.
  * All node-major tensors are in PLAN order.  Co in {64,128,256}; layer.kin == Co; layer.nout <= 512;
  * K <= 40; every tile's distinct-row count <= min(umax, cp_edgeconv_ring_rows(KP)) (else use
  * cp_chain_fwd(CP_PRO_AGG)). */
@@ -203,7 +203,10 @@ int cp_edgeconv_fwd(const cp_edgeconv_params* p, cp_stream_t s);
 
 /* ---- K3: Index2Feat 4-tap integer gather (pipeline.py:156-163) + roi-mask multiply (:280) ------
  * patches (B, Hp, Wp, E) NHWC in `dtype`; taps (2y,2x),(2y+k,2x),(2y,2x+k),(2y+k,2x+k), channel order
- * [tap1 | tap2 | tap3 | tap4]; out (B, N, 4E) node-major in `dtype`; mask (B,N) f32 or NULL. */
+ * [tap1 | tap2 | tap3 | tap4]; out (B, N, 4E) node-major in `dtype`; mask (B,N) f32 or NULL.
+ * Precondition (as for the CP_PRO_TAPS prologue of cp_chain_fwd): 0 <= 2*id and 2*id + tap_step < Hp / Wp.  An id
+ * outside the patch map traps the kernel (the reference's indexing raises a device-side assert); nothing is read
+ * out of bounds. */
 int cp_sample_taps(const void* patches, int dtype, int Hp, int Wp, int E, int tap_step, const int64_t* x_id,
                    const int64_t* y_id, const float* mask, void* out, int B, int N, cp_stream_t s);
 
@@ -222,6 +225,10 @@ int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_
  * Logit rows, roi_mask and ids are in PLAN order (row n of RoI b is keypoint perm[g(b)][n]; perm (G,N) int32 from
  * cp_graph_plan_build, graph_sel (B) int32 or NULL => graph 0; perm NULL => identity); roi_bit / x_bits / y_bits
  * are written in the reference's keypoint order. */
+/* 1-based object ids (n) int64 -> 0-based graph selector int32 (pipeline_lm.py:56-57: self.knn_idx[obj_ids-1]).
+ * An id outside [1, G] traps on the device -- the reference raises a device-side index assert for it. */
+int cp_graph_sel(const int64_t* obj_ids, int64_t n, int G, int32_t* out, cp_stream_t s);
+
 int cp_decode_init(const float* logits, int ld, int L, int Ltot, float* roi_bit, float* x_bits, float* y_bits,
                    float* roi_mask, int64_t* x_id, int64_t* y_id, int B, int N, const int32_t* perm,
                    const int32_t* graph_sel, cp_stream_t s);

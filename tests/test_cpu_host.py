@@ -269,3 +269,44 @@ def test_graph_plan_without_coordinates_keeps_order():
     idx = torch.randint(0, 2000, (1, 2000, 12), generator=g, dtype=torch.int32)
     plan = ops.GraphPlan(idx, None)
     assert plan.identity and torch.equal(plan.idx_p, idx) and not plan.staged   # random graph: too many distinct rows
+
+
+def test_cache_keys_tolerate_inference_tensors():
+    """tensors created under torch.inference_mode() raise when ``_version`` is read; the prepared-weight and
+    graph caches must not."""
+    from checkerpose_b200 import head
+    with torch.inference_mode():
+        lin = torch.nn.Linear(8, 4)
+        t = torch.arange(6).view(1, 2, 3)
+    assert t.is_inference()
+    with pytest.raises(RuntimeError):
+        t._version
+    assert head._ver(t) == -1 and head._ver(torch.zeros(2)) == 0
+    fp = head._param_fingerprint(lin)
+    assert len(fp) == 2 and fp == head._param_fingerprint(lin)
+
+
+def test_rgb_image_to_class_id_image():
+    from checkerpose_b200.binary_code_helper import class_id_encoder_decoder as codec
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(5, 7, 3), dtype=np.uint8)
+    ids = codec.RGB_image_to_class_id_image(img)
+    want = img[..., 0].astype(np.int64) * 65536 + img[..., 1].astype(np.int64) * 256 + img[..., 2].astype(np.int64)
+    assert ids.shape == (5, 7) and np.array_equal(ids, want)
+
+
+def test_product_package_does_not_read_tests_dir():
+    pkg = os.path.join(REPO, "checkerpose_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py") and "make_fps_fixture" not in f:
+                src = open(os.path.join(root, f)).read()
+                assert '"tests"' not in src and "'tests'" not in src, f"{f} refers to the tests directory"
+    assert os.path.exists(syn.FPS_FIXTURE) and os.sep + "tests" + os.sep not in syn.FPS_FIXTURE
+
+
+def test_negative_leaky_slope_is_rejected_by_the_fold():
+    """lrelu(max_k P + Q) == max_k lrelu(P + Q) needs an increasing activation."""
+    from checkerpose_b200 import head
+    src = open(os.path.join(REPO, "checkerpose_b200", "head.py")).read()
+    assert "negative_slope >= 0" in src and hasattr(head, "PreparedEdgeConv")

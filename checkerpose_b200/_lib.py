@@ -78,6 +78,8 @@ SIGNATURES = {
     "cp_graph_plan_build": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cp_edgeconv_fwd": (c_i32, [C.POINTER(EdgeConvParams), c_vp]),
     "cp_correspondences": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "cp_correspondences_pack": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "cp_correspondences_unpack": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cp_fps": (c_i32, [c_vp, c_i32, c_i32, C.POINTER(C.c_double), C.c_double, c_vp, c_vp, c_vp, c_vp]),
     "cp_threshold": (c_i32, [c_vp, c_f32, c_i32, c_vp, c_i32, c_i64, c_vp]),
     "cp_id_to_bits": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),

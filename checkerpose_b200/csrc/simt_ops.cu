@@ -431,6 +431,47 @@ __global__ void correspondences_kernel(const float* __restrict__ roi_bit, const 
   }
 }
 
+// Packed form of the same records for the multi-GPU gather / the device->host read-back: per RoI one row of
+// 16 + 2 N bytes = { f32 bbox[4]; u16 rec[N] }, rec = x_id | y_id << 6 | flags << 12 (S <= 64).  u, v are an affine
+// function of (bbox, id) that the consumer evaluates (cp_correspondences_unpack, or numpy on the host).
+__global__ void correspondences_pack_kernel(const float* __restrict__ roi_bit, const float* __restrict__ seg,
+                                            const float* __restrict__ bbox, const int64_t* __restrict__ x_id,
+                                            const int64_t* __restrict__ y_id, uint8_t* __restrict__ out, int B, int N, int S) {
+  const int64_t total = (int64_t)B * N;
+  const size_t row_bytes = 16 + 2 * (size_t)N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / N), n = (int)(e - (int64_t)b * N);
+    const int xi = (int)x_id[e], yi = (int)y_id[e];
+    uint32_t f = roi_bit[e] > 0.f ? 1u : 0u;
+    if (f) {
+      const size_t pix = (size_t)yi * S + xi;
+      const float* sb = seg + (size_t)b * 2 * S * S;
+      if (sb[(size_t)S * S + pix] > 0.f) f |= 2u;
+      if (sb[pix] > 0.f) f |= 4u;
+    }
+    uint8_t* row = out + (size_t)b * row_bytes;
+    reinterpret_cast<uint16_t*>(row + 16)[n] = (uint16_t)((uint32_t)xi | ((uint32_t)yi << 6) | (f << 12));
+    if (n < 4) reinterpret_cast<float*>(row)[n] = bbox[(size_t)b * 4 + n];
+  }
+}
+
+__global__ void correspondences_unpack_kernel(const uint8_t* __restrict__ packed, cp_corr_record* __restrict__ out, int B, int N, int S) {
+  const int64_t total = (int64_t)B * N;
+  const size_t row_bytes = 16 + 2 * (size_t)N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / N), n = (int)(e - (int64_t)b * N);
+    const uint8_t* row = packed + (size_t)b * row_bytes;
+    const float* bb = reinterpret_cast<const float*>(row);
+    const uint32_t w = reinterpret_cast<const uint16_t*>(row + 16)[n];
+    const int xi = w & 63, yi = (w >> 6) & 63;
+    cp_corr_record r;   // the same fp64 arithmetic as correspondences_kernel: bit-identical u, v
+    r.u = (float)(((double)bb[2] / (double)S) * (double)xi + (double)bb[0]);
+    r.v = (float)(((double)bb[3] / (double)S) * (double)yi + (double)bb[1]);
+    r.flags = w >> 12;
+    out[e] = r;
+  }
+}
+
 __global__ void threshold_kernel(const float* __restrict__ x, float thr, int apply_sigmoid, void* __restrict__ out,
                                  int out_dtype, int64_t n) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -682,6 +723,23 @@ int cp_correspondences(const float* roi_bit, const float* seg, const float* bbox
              "cp_correspondences: bad arguments");
   correspondences_kernel<<<grid_for((int64_t)B * N), 256, 0, (cudaStream_t)s>>>(roi_bit, seg, bbox, x_id, y_id, out, B, N, S);
   CP_CHECK_LAUNCH("cp_correspondences");
+  return CP_OK;
+}
+
+int cp_correspondences_pack(const float* roi_bit, const float* seg, const float* bbox, const int64_t* x_id,
+                            const int64_t* y_id, uint8_t* out, int B, int N, int S, cp_stream_t s) {
+  CP_REQUIRE(roi_bit && seg && bbox && x_id && y_id && out && B > 0 && N > 0, CP_E_INVALID, "cp_correspondences_pack: bad arguments");
+  CP_REQUIRE(S > 0 && S <= 64 && N >= 4 && N % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0, CP_E_UNSUPPORTED,
+             "cp_correspondences_pack: needs S <= 64 (6-bit ids), even N >= 4, 4-byte aligned rows (S=%d N=%d)", S, N);
+  correspondences_pack_kernel<<<grid_for((int64_t)B * N), 256, 0, (cudaStream_t)s>>>(roi_bit, seg, bbox, x_id, y_id, out, B, N, S);
+  CP_CHECK_LAUNCH("cp_correspondences_pack");
+  return CP_OK;
+}
+
+int cp_correspondences_unpack(const uint8_t* packed, cp_corr_record* out, int B, int N, int S, cp_stream_t s) {
+  CP_REQUIRE(packed && out && B > 0 && N > 0 && S > 0 && S <= 64 && N % 2 == 0, CP_E_INVALID, "cp_correspondences_unpack: bad arguments");
+  correspondences_unpack_kernel<<<grid_for((int64_t)B * N), 256, 0, (cudaStream_t)s>>>(packed, out, B, N, S);
+  CP_CHECK_LAUNCH("cp_correspondences_unpack");
   return CP_OK;
 }
 

@@ -73,3 +73,35 @@ def gather_correspondences(records: torch.Tensor, total: int | None = None, grou
         return out
     out = out.view((world, bmax) + tuple(records.shape[1:]))
     return torch.cat([out[r, :sizes[r]] for r in range(world)], dim=0)
+
+
+class OverlappedGather:
+    """The all-gather of a step's records on a side stream, overlapped with the next step's compute.
+
+    ``submit(records)`` orders the collective after everything enqueued so far on the current (compute) stream, runs it
+    on the gather stream into one of ``depth`` rotating output buffers and returns ``(gathered, done_event)`` without
+    blocking the compute stream; a consumer on another stream waits on ``done_event``.  With one rank it returns the
+    records themselves.  The caller must ``torch.cuda.synchronize()`` (or wait on the events) before the results of the
+    last steps count as delivered -- bench.py's timed regions end with exactly that."""
+
+    def __init__(self, device, depth: int = 2, group=None):
+        self.device, self.depth, self.group = torch.device(device), depth, group
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._events = [None] * depth
+        self._i = 0
+
+    def submit(self, records: torch.Tensor, total: int | None = None):
+        done = torch.cuda.Event()
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            done.record(torch.cuda.current_stream(self.device))
+            return records, done
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            records.record_stream(self.stream)
+            out = gather_correspondences(records, total, self.group)
+            done.record(self.stream)
+        self._events[self._i % self.depth] = done
+        self._i += 1
+        return out, done

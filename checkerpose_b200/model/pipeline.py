@@ -284,12 +284,13 @@ class PoseNet_GNNskip(head.DeviceScopedModule):
                 graph_feat_dim=graph_feat_dim_i))
         self.seg_block = nn.Conv2d(num_filters, seg_output_dim, kernel_size=1, padding=0, bias=True)
 
-    def forward_with_correspondences(self, img, p3d_normed, bbox, stage=None, obj_ids=None):
+    def forward_with_correspondences(self, img, p3d_normed, bbox, stage=None, obj_ids=None, packed=False):
         """Extension: the reference's 6-tuple plus (B,N,3) int32 correspondence records
-        {f32 u, f32 v, u32 flags} (first half of from_id_to_pose, test_network_with_test_data.py:50-66)."""
+        {f32 u, f32 v, u32 flags} (first half of from_id_to_pose, test_network_with_test_data.py:50-66);
+        ``packed``: the 2-byte-per-keypoint rows of ops.correspondences_packed instead."""
         img_feats = self.init_net.img_backbone(img)
         with torch.cuda.device(img_feats[-1].device):
-            return head.pose_head_forward(self, img_feats, obj_ids=obj_ids, stage=stage, bbox=bbox)
+            return head.pose_head_forward(self, img_feats, obj_ids=obj_ids, stage=stage, bbox=bbox, packed=packed)
 
     def forward(self, img, p3d_normed, stage=None):
         img_feats = self.init_net.img_backbone(img)

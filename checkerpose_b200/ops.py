@@ -464,6 +464,52 @@ def correspondences(roi_bit, seg, bbox, x_id, y_id, out=None):
     return out
 
 
+def packed_row_bytes(N: int) -> int:
+    return 16 + 2 * int(N)
+
+
+def correspondences_packed(roi_bit, seg, bbox, x_id, y_id, out=None):
+    """-> (B, 16 + 2N) uint8 rows {f32 bbox[4]; u16 rec[N]}, rec = x_id | y_id << 6 | flags << 12 (cp_correspondences_pack):
+    the payload of the multi-GPU gather and of the device->host read-back, 2 bytes per keypoint."""
+    _need_cuda(roi_bit, seg, bbox, x_id, y_id)
+    B, N = x_id.shape
+    S = seg.shape[-1]
+    assert seg.shape[1] == 2 and seg.is_contiguous() and roi_bit.is_contiguous() and bbox.shape == (B, 4)
+    if out is None:
+        out = torch.empty((B, packed_row_bytes(N)), dtype=torch.uint8, device=x_id.device)
+    check(lib.cp_correspondences_pack(_p(roi_bit), _p(seg.float()), _p(bbox.contiguous().float()), _p(x_id), _p(y_id), _p(out),
+                                      B, N, S, _stream()), "cp_correspondences_pack")
+    _count()
+    return out
+
+
+def unpack_correspondences(packed: torch.Tensor, S: int = 64, out=None):
+    """(B, 16 + 2N) uint8 packed rows (CUDA) -> (B,N,3) int32 records, bit-identical to ``correspondences``."""
+    _need_cuda(packed)
+    assert packed.dtype == torch.uint8 and packed.is_contiguous()
+    B = packed.shape[0]
+    N = (packed.shape[1] - 16) // 2
+    if out is None:
+        out = torch.empty((B, N, 3), dtype=torch.int32, device=packed.device)
+    check(lib.cp_correspondences_unpack(_p(packed), _p(out), B, N, int(S), _stream()), "cp_correspondences_unpack")
+    _count()
+    return out
+
+
+def unpack_correspondences_host(packed, S: int = 64):
+    """Host-side consumer of the packed rows (numpy; the PnP stage that reads them runs on the CPU):
+    (B, 16 + 2N) uint8 -> (uv (B,N,2) float32, flags (B,N) int32, x_id, y_id (B,N) int32, bbox (B,4) float32)."""
+    import numpy as np
+    a = np.ascontiguousarray(packed.cpu().numpy() if isinstance(packed, torch.Tensor) else packed)
+    bbox = a[:, :16].copy().view(np.float32)
+    w = a[:, 16:].copy().view(np.uint16).astype(np.int32)
+    x_id, y_id, flags = w & 63, (w >> 6) & 63, w >> 12
+    bb = bbox.astype(np.float64)
+    u = (bb[:, 2:3] / S) * x_id + bb[:, 0:1]
+    v = (bb[:, 3:4] / S) * y_id + bb[:, 1:2]
+    return np.stack([u, v], axis=-1).astype(np.float32), flags, x_id, y_id, bbox
+
+
 def split_correspondences(rec: torch.Tensor):
     """(…,3) int32 records -> (uv float32 (…,2), flags int32 (…))."""
     uv = rec[..., :2].contiguous().view(torch.float32)

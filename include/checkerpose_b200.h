@@ -250,6 +250,13 @@ int cp_permute_rows(const void* src, void* dst, int row_bytes, int B, int N, con
 typedef struct { float u, v; uint32_t flags; } cp_corr_record;
 int cp_correspondences(const float* roi_bit, const float* seg, const float* bbox, const int64_t* x_id,
                        const int64_t* y_id, cp_corr_record* out, int B, int N, int S, cp_stream_t s);
+/* The same records packed for the multi-GPU gather and the device->host read-back (2 bytes per keypoint instead
+ * of 12): per RoI one row of 16 + 2 N bytes = { f32 bbox[4]; u16 rec[N] }, rec = x_id | y_id << 6 | flags << 12.
+ * Needs S <= 64 (6-bit ids) and an even N >= 4.  cp_correspondences_unpack evaluates u, v with the arithmetic of
+ * cp_correspondences (bit-identical records). */
+int cp_correspondences_pack(const float* roi_bit, const float* seg, const float* bbox, const int64_t* x_id,
+                            const int64_t* y_id, uint8_t* out, int B, int N, int S, cp_stream_t s);
+int cp_correspondences_unpack(const uint8_t* packed, cp_corr_record* out, int B, int N, int S, cp_stream_t s);
 
 /* Elementwise helpers behind common_ops.py:5-27 and pipeline.py:84-127.
  * out = sigmoid(x) > thr ? 1 : 0 as f32 (out_dtype 0) or int64 (out_dtype 1). */

@@ -198,9 +198,15 @@ def test_bench_reference_arm_contract():
     spec = importlib.util.spec_from_file_location("bench", os.path.join(REPO, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    assert bench.METRIC.startswith("RoIs/sec") and bench.NPOINT == 4096
-    hbm, src = bench.load_peaks()
-    assert hbm > 1000 and ("measured" in src or "fallback" in src)
+    assert bench.METRIC.startswith("RoIs/sec") and "4096" in bench.METRIC
+    hbm, tf_burst, tf_sus, src = bench.load_peaks()
+    assert hbm > 1000 and tf_burst >= tf_sus > 100 and ("measured" in src or "fallback" in src)
+    # every BASELINE config is a workload of the bench; the default is configs[2]
+    import argparse
+    for name, per_gpu, scaling in (("full4096", 256, "weak"), ("init64", 64, "weak"), ("ycbv1024", 128, "strong"), ("lm_sweep", 256, "weak")):
+        wl = bench.workload(argparse.Namespace(config=name, npoint=0, graph_k=0, batch=0), world=8)
+        assert wl["per_gpu"] == per_gpu and wl["scaling"] == scaling
+    assert bench.LM_OBJECT_IDS == (1, 2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15)
 
 
 # ------------------------------------------------------------------------------------------------ graph plan (host code)

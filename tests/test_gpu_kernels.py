@@ -250,6 +250,25 @@ def test_correspondences(cp, golden):
             assert np.allclose(uv[c][m], g[f"c{c}_{tag}_p2d"], rtol=1e-6, atol=0)  # f32 record vs f64 grid
 
 
+def test_correspondences_packed_roundtrip(cp):
+    """The 2-byte records that cross NVLink / PCIe decode to exactly the 12-byte records (device kernel and host numpy)."""
+    B, N, S = 5, 4096, 64
+    g = torch.Generator().manual_seed(11)
+    roi = torch.randn(B, 1, N, generator=g).cuda()
+    seg = torch.randn(B, 2, S, S, generator=g).cuda()
+    bbox = syn.synthetic_bboxes(B, g).cuda()
+    xid = torch.randint(0, S, (B, N), generator=g).cuda()
+    yid = torch.randint(0, S, (B, N), generator=g).cuda()
+    rec = cp.ops.correspondences(roi, seg, bbox, xid, yid)
+    packed = cp.ops.correspondences_packed(roi, seg, bbox, xid, yid)
+    assert packed.shape == (B, 16 + 2 * N) and packed.dtype == torch.uint8
+    assert torch.equal(cp.ops.unpack_correspondences(packed, S), rec)
+    uv, flags, x2, y2, bb = cp.ops.unpack_correspondences_host(packed, S)
+    uv_ref, flags_ref = cp.ops.split_correspondences(rec)
+    assert np.array_equal(uv, uv_ref.cpu().numpy()) and np.array_equal(flags, flags_ref.cpu().numpy())
+    assert np.array_equal(x2, xid.cpu().numpy()) and np.array_equal(y2, yid.cpu().numpy()) and np.array_equal(bb, bbox.cpu().numpy())
+
+
 # ------------------------------------------------------------------------------------------------ tcgen05 chain
 def _bf16_round(t):
     return t.to(torch.bfloat16).float()

@@ -48,11 +48,26 @@ class EdgeConvParams(C.Structure):
     ]
 
 
+class GemmX3Params(C.Structure):
+    _fields_ = [
+        ("mode", c_i32),
+        ("a1", c_vp), ("ld1", c_i32), ("k1", c_i32),
+        ("a2", c_vp), ("ld2", c_i32), ("k2", c_i32),
+        ("H", c_i32), ("W", c_i32), ("Ho", c_i32), ("Wo", c_i32), ("KH", c_i32), ("KW", c_i32), ("pad", c_i32),
+        ("M", c_i64), ("K", c_i32),
+        ("w_hi", c_vp), ("w_lo", c_vp),
+        ("bias", c_vp), ("act", c_i32), ("slope", c_f32),
+        ("out", c_vp), ("ld_out", c_i32), ("Nout", c_i32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol of include/checkerpose_b200.h
 SIGNATURES = {
     "cp_last_error_string": (C.c_char_p, []),
     "cp_version": (c_i32, []),
     "cp_device_arch": (c_i32, []),
+    "cp_pack_weight_split": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "cp_gemm_x3": (c_i32, [C.POINTER(GemmX3Params), c_vp]),
     "cp_graph_sel": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "cp_knn": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp_transpose_cn_to_nc": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

@@ -4,13 +4,15 @@ This is the engine shared by the drop-in modules in ``checkerpose_b200/model``: 
 (EdgeConv folding, bf16 tile packing, BN folding of the image branch) and the node-major forward of
 the init head, one refine stage and the whole progressive head.  Two compute modes:
 
-* ``torch.float32``  -- validation mode: FFMA GEMMs (``cp_linear_f32``), fp32 aggregation; matches the
-  reference to ~1e-5 and decodes bit-exactly outside the 1e-4 logit band.
+* ``torch.float32``  -- exact mode: fp32 tensors in HBM; every GEMM and every convolution of the image branch on the
+  tensor cores with operands split into bf16 hi + lo (``cp_gemm_x3``: three tcgen05.mma per product, ~2^-16 relative),
+  fp32 aggregation; matches the reference to ~1e-5 and decodes bit-exactly outside the 1e-4 logit band.
 * ``torch.bfloat16`` -- product mode: the fused tcgen05 chain kernel (``cp_chain_fwd``), bf16 tensors in
   HBM, fp32 accumulation in TMEM.
 
-The image branch (``up_net``, ``patch_generator``, ``seg_block``, ``conv1x1``) is dense convolution and
-stays on cuDNN/cuBLAS through torch, as SURVEY.md section 8 marks it (library part of the path).
+The image branch (``up_net``, ``patch_generator``, ``seg_block``, ``conv1x1``) is dense convolution: in bf16 mode it
+stays on cuDNN/cuBLAS through torch, as SURVEY.md section 8 marks it (library part of the path); in float32 mode it runs
+on the implicit-GEMM form of ``cp_gemm_x3``.
 """
 from __future__ import annotations
 
@@ -39,30 +41,28 @@ def get_compute_dtype():
     return _COMPUTE_DTYPE
 
 
-@contextlib.contextmanager
-def _exact_fp32_convs(enabled: bool):
-    """fp32 validation mode must not silently run cuDNN convolutions in TF32."""
-    if not enabled:
-        yield
-        return
-    old_c, old_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        yield
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_c, old_m
-
-
 # --------------------------------------------------------------------------------------------------
 # prepared weights (derived from the module parameters; never stored in the state_dict)
 # --------------------------------------------------------------------------------------------------
 class PreparedLinear:
+    """bf16 mode: ``packed`` = bf16 tile image for the chain / EdgeConv kernels.  float32 mode: ``split`` = the
+    (hi, lo) bf16 tile images of the split-precision tensor-core GEMM (cp_gemm_x3); layers whose K is not a multiple
+    of 64 (none of the shipped shapes) keep the SIMT GEMM."""
+
     def __init__(self, weight, bias, want_packed):
         self.w = weight.detach().reshape(weight.shape[0], -1).contiguous().float()
         self.b = None if bias is None else bias.detach().contiguous().float()
         self.nout, self.kin = self.w.shape
         self.packed = ops.pack_weight(self.w) if (want_packed and self.kin % 64 == 0) else None
+        self.split = ops.pack_weight_split(self.w) if (not want_packed and self.kin % 64 == 0 and self.w.is_cuda) else None
+
+
+def linear32(x, prep: "PreparedLinear", act=False, slope=0.0, a2=None):
+    """float32 mode: y = act([x|a2] @ W.T + b) -- split-bf16 x3 on tcgen05 when the shape allows, else SIMT FFMA."""
+    k2 = 0 if a2 is None else a2.shape[-1]
+    if prep.split is not None and x.shape[-1] % 64 == 0 and k2 % 64 == 0:
+        return ops.gemm_x3_linear(x, prep.split, prep.nout, prep.b, act, slope, a2=a2)
+    return ops.linear_f32(x, prep.w, prep.b, act, slope, a2=a2)
 
 
 class PreparedEdgeConv(PreparedLinear):
@@ -245,7 +245,7 @@ def edgeconv_node_major(sg_module, x_nm, ctx: GraphCtx, dtype):
     prep = prepared_edgeconv(sg_module, dtype)
     B, N, C = x_nm.shape
     if dtype == torch.float32:
-        z = ops.linear_f32(x_nm, prep.w, prep.b)
+        z = linear32(x_nm, prep)
         return ops.edge_aggregate(z, ctx.plan.idx_p, ctx.sel, prep.slope)
     if not (_chain_ok(C) and _chain_ok(prep.Co)):
         raise RuntimeError(f"bf16 EdgeConv supports C, C' in {{64,128,256}} (got {C}->{prep.Co}); use float32 mode")
@@ -266,12 +266,11 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
     N = init_net.npoint
     dev = feat_last.device
     bias0 = None
-    with _exact_fp32_convs(dtype == torch.float32):
-        if dtype == torch.bfloat16:
-            conv = _bf16_module(init_net.conv1x1)
-            x0, bias0 = conv(feat_last.to(torch.bfloat16), defer_last_bias=True)   # bias applied by the layout change below
-        else:
-            x0 = init_net.conv1x1(feat_last.float())
+    if dtype == torch.bfloat16:
+        conv = _bf16_module(init_net.conv1x1)
+        x0, bias0 = conv(feat_last.to(torch.bfloat16), defer_last_bias=True)   # bias applied by the layout change below
+    else:
+        x0 = image_block(init_net.conv1x1, feat_last, dtype)                   # 1x1 conv = split-precision GEMM, NHWC result
     blocks = list(init_net.pre_query_block)
     mlp = prepared_linear(init_net.mlp, dtype)
     nbits = mlp.nout
@@ -286,13 +285,16 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
     else:
         if bias0 is not None:
             x0 = x0 + bias0.to(x0.dtype).view(1, -1, 1, 1)
-        x = x0.contiguous().view(B, N, hw)
+        if x0.permute(0, 2, 3, 1).is_contiguous():      # NHWC storage (B,hw,N) -> (B,N,hw) with the tiled transpose
+            x = ops.to_node_major(x0.permute(0, 2, 3, 1).reshape(B, hw, N), x0.dtype)
+        else:
+            x = x0.contiguous().view(B, N, hw)
         if ctx is not None:
             x = ctx.to_plan(x)
     if dtype == torch.float32:
         for blk in blocks:
             x = edgeconv_node_major(blk, x, ctx, dtype)
-        logits = ops.linear_f32(x, mlp.w, mlp.b)
+        logits = linear32(x, mlp)
         return logits, x, ctx
     # bf16: LOAD->[W_0] ; AGG->[W_j] ... ; AGG(+store feature)->[mlp]
     logits = torch.empty((B, N, 16), dtype=torch.float32, device=dev)
@@ -436,6 +438,92 @@ class _FoldedSeq:
         return (x, None) if defer_last_bias else x
 
 
+class _X3Seq:
+    """float32 mode of an image-branch conv stack (up_net block, patch_generator, seg_block, conv1x1): BatchNorm folded
+    into the weights, every convolution an implicit GEMM of the split-precision tensor-core kernel (cp_gemm_x3) over
+    NHWC fp32 maps with bias + ReLU in its epilogue; the bilinear x2 upsampling of the concatenated skip connection runs
+    on cp_upsample2x_cat_nhwc.  NCHW in, NCHW (channels_last strides) out."""
+
+    def __init__(self, module):
+        mods = list(module) if isinstance(module, nn.Sequential) else [module]
+        self.ops = []
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                tr = isinstance(m, nn.ConvTranspose2d)
+                w = m.weight.detach().float()
+                b = None if m.bias is None else m.bias.detach().float()
+                if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d):
+                    bn = mods[i + 1]
+                    sc = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+                    sh = bn.bias.detach().float() - sc * bn.running_mean.detach().float()
+                    w = w * (sc.view(1, -1, 1, 1) if tr else sc.view(-1, 1, 1, 1))
+                    b = sh if b is None else b * sc + sh
+                    i += 1
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                if relu:
+                    i += 1
+                kh, kw = m.kernel_size
+                ok = (m.groups == 1 and tuple(m.dilation) == (1, 1) and m.padding[0] == m.padding[1] and
+                      (tuple(m.stride) == ((2, 2) if tr else (1, 1))) and (not tr or tuple(m.output_padding) == (1, 1)))
+                cin, cout = (w.shape[0], w.shape[1]) if tr else (w.shape[1], w.shape[0])
+                if not ok or cin % 64 != 0:
+                    raise RuntimeError(f"float32 image branch: unsupported convolution {m}")
+                wm = (w.permute(1, 2, 3, 0) if tr else w.permute(0, 2, 3, 1)).reshape(cout, kh * kw * cin).contiguous()
+                self.ops.append(("convT" if tr else "conv", ops.pack_weight_split(wm), None if b is None else b.contiguous(),
+                                 (cout, kh, kw, int(m.padding[0])), relu))
+            elif isinstance(m, nn.UpsamplingBilinear2d):
+                if float(m.scale_factor) != 2.0:
+                    raise RuntimeError("image branch: only UpsamplingBilinear2d(scale_factor=2) is supported")
+                self.ops.append(("up", None, None, None, False))
+            elif isinstance(m, nn.ReLU):
+                self.ops.append(("relu", None, None, None, False))
+            else:
+                raise RuntimeError(f"unsupported layer in image branch: {type(m).__name__}")
+            i += 1
+
+    @staticmethod
+    def _nhwc(x):
+        """NCHW fp32 (any strides) -> contiguous (B,H,W,C)."""
+        v = x.permute(0, 2, 3, 1)
+        if v.is_contiguous():
+            return v
+        B, Cc, H, W = x.shape
+        return ops.to_node_major(x.contiguous().view(B, Cc, H * W), torch.float32).view(B, H, W, Cc)
+
+    def __call__(self, x, skip=None):
+        start = 0
+        if self.ops[0][0] == "up":
+            a = self._nhwc(x).permute(0, 3, 1, 2)
+            s = None if skip is None else self._nhwc(skip).permute(0, 3, 1, 2)
+            y = ops.upsample2x_cat(a, s).permute(0, 2, 3, 1)         # (B,2H,2W,Ca+Cb) contiguous
+            start = 1
+        else:
+            if skip is not None:
+                x = torch.cat([x, skip], dim=1)
+            y = self._nhwc(x)
+        for kind, ws, b, geom, relu in self.ops[start:]:
+            if kind in ("conv", "convT"):
+                cout, kh, kw, pad = geom
+                H, W = y.shape[1], y.shape[2]
+                if kind == "conv":
+                    Ho, Wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+                else:
+                    Ho, Wo = (H - 1) * 2 - 2 * pad + kh + 1, (W - 1) * 2 - 2 * pad + kw + 1
+                y = ops.gemm_x3_conv(y, ws, cout, kh, kw, pad, Ho, Wo, b, relu, 0.0, transposed=(kind == "convT"))
+            elif kind == "relu":
+                y = torch.relu_(y)
+            else:
+                y = ops.upsample2x_cat(y.permute(0, 3, 1, 2), None).permute(0, 2, 3, 1)
+        return y.permute(0, 3, 1, 2)
+
+
+def _x3_module(module):
+    _require_eval(module)
+    return _PREP.get(module, ("x3seq",), lambda: _X3Seq(module))
+
+
 def _bf16_module(module):
     _require_eval(module)
     return _PREP.get(module, ("bf16seq",), lambda: _FoldedSeq(module))
@@ -463,13 +551,10 @@ def image_block(module, x, dtype, skip=None):
     to ``x`` along the channels first (pipeline.py:372)."""
     if _IMG_REUSE is not None and id(module) in _IMG_REUSE:
         return _IMG_REUSE[id(module)]
-    with _exact_fp32_convs(dtype == torch.float32):
-        if dtype == torch.bfloat16:
-            y = _bf16_module(module)(x.to(torch.bfloat16), None if skip is None else skip.to(torch.bfloat16))
-        else:
-            if skip is not None:
-                x = torch.cat([x.float(), skip.float()], dim=1)
-            y = module(x.float())
+    if dtype == torch.bfloat16:
+        y = _bf16_module(module)(x.to(torch.bfloat16), None if skip is None else skip.to(torch.bfloat16))
+    else:
+        y = _x3_module(module)(x.float(), None if skip is None else skip.float())
     if _IMG_REUSE is not None:
         _IMG_REUSE[id(module)] = y
     return y
@@ -502,13 +587,13 @@ def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, ctx, dtype)
     y_id = y_id.contiguous()
     if dtype == torch.float32:
         taps = ops.sample_taps(patches, x_id, y_id, roi_mask, k)
-        h = ops.linear_f32(taps, pg0.w, pg0.b, True, slope, a2=gfeat_nm)
-        h = ops.linear_f32(h, pg1.w, pg1.b, True, slope)
+        h = linear32(taps, pg0, True, slope, a2=gfeat_nm)
+        h = linear32(h, pg1, True, slope)
         for blk in blocks:
             h = edgeconv_node_major(blk, h, ctx, dtype)
-        t = ops.linear_f32(h, q[0].w, q[0].b, True, qslope)
-        t = ops.linear_f32(t, q[1].w, q[1].b, True, qslope)
-        logits = ops.linear_f32(t, q[2].w, q[2].b)
+        t = linear32(h, q[0], True, qslope)
+        t = linear32(t, q[1], True, qslope)
+        logits = linear32(t, q[2])
         return logits, h
     # ---- bf16 fused kernels ----
     E = patches.shape[-1]
@@ -571,7 +656,7 @@ def mlp_node_major(mods, x_nm, dtype, out_f32=False):
         x = x_nm
         for lin, act, slope in layers:
             pl = prepared_linear(lin, dtype)
-            x = ops.linear_f32(x, pl.w, pl.b, act, slope)
+            x = linear32(x, pl, act, slope)
         return x
     x = x_nm
     for j0 in range(0, len(layers), 3):

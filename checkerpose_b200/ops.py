@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ChainLayer, ChainParams, EdgeConvParams, GraphPlanStruct, check, lib
+from ._lib import ChainLayer, ChainParams, EdgeConvParams, GemmX3Params, GraphPlanStruct, check, lib
 
 CP_F32, CP_BF16 = 0, 1
 PRO_LOAD, PRO_AGG, PRO_TAPS = 0, 1, 2
@@ -190,7 +190,84 @@ def pack_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
-# ------------------------------------------------------------------------------------ fp32 path
+# ------------------------------------------------------------------- float32 mode on tcgen05 (split bf16 x 3)
+X3_LINEAR, X3_CONV, X3_CONVT = 0, 1, 2
+
+
+def pack_weight_split(w: torch.Tensor):
+    """(Nout,K) f32 -> (packed bf16(w), packed bf16(w - bf16(w))) tile images for cp_gemm_x3."""
+    _need_cuda(w)
+    w = w.contiguous().float()
+    Nout, K = w.shape
+    nbytes = lib.cp_packed_weight_bytes(Nout, K)
+    if nbytes == 0:
+        raise RuntimeError(f"pack_weight_split: unsupported shape ({Nout},{K}); K must be a multiple of 64")
+    hi = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+    lo = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+    check(lib.cp_pack_weight_split(_p(w), Nout, K, _p(hi), _p(lo), _stream()), "cp_pack_weight_split")
+    _count()
+    return hi, lo
+
+
+def _gemm_x3(p: GemmX3Params, sig):
+    if chain_event_log is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.cp_gemm_x3(C.byref(p), _stream()), "cp_gemm_x3")
+        e1.record()
+        chain_event_log.append((sig, e0, e1))
+    else:
+        check(lib.cp_gemm_x3(C.byref(p), _stream()), "cp_gemm_x3")
+    _count()
+
+
+def gemm_x3_linear(a1, w_split, nout, bias=None, act=False, slope=0.0, a2=None, out=None):
+    """y = act([a1|a2] @ W.T + bias) in float32 on the tensor cores (cp_gemm_x3, CP_X3_LINEAR); a* (..., K*) fp32 rows."""
+    _need_cuda(a1, a2, bias, w_split[0], w_split[1])
+    assert a1.dtype == torch.float32 and a1.stride(-1) == 1
+    a1 = a1 if a1.is_contiguous() else a1.contiguous()
+    K1 = a1.shape[-1]
+    M = a1.numel() // K1
+    K2 = 0
+    if a2 is not None:
+        assert a2.dtype == torch.float32
+        a2 = a2 if a2.is_contiguous() else a2.contiguous()
+        K2 = a2.shape[-1]
+    if out is None:
+        out = torch.empty(a1.shape[:-1] + (nout,), dtype=torch.float32, device=a1.device)
+    p = GemmX3Params()
+    p.mode = X3_LINEAR
+    p.a1, p.ld1, p.k1 = _p(a1), K1, K1
+    p.a2, p.ld2, p.k2 = _p(a2), K2, K2
+    p.M, p.K = M, K1 + K2
+    p.w_hi, p.w_lo = _p(w_split[0]), _p(w_split[1])
+    p.bias, p.act, p.slope = _p(bias), int(bool(act)), float(slope)
+    p.out, p.ld_out, p.Nout = _p(out), out.stride(-2) if out.dim() > 1 else nout, int(nout)
+    _gemm_x3(p, ("X3", K1 + K2, (int(nout),), OUT_F32, M, 0))
+    return out
+
+
+def gemm_x3_conv(x_nhwc, w_split, nout, KH, KW, pad, Ho, Wo, bias=None, act=False, slope=0.0, transposed=False):
+    """Conv2d KH x KW stride 1 / ConvTranspose2d stride 2 over an fp32 NHWC map (B,H,W,Cin) -> (B,Ho,Wo,nout) fp32, as an
+    implicit GEMM on the tensor cores (cp_gemm_x3, CP_X3_CONV / CP_X3_CONVT); W rows in (ky, kx, c) order."""
+    _need_cuda(x_nhwc, bias, w_split[0], w_split[1])
+    assert x_nhwc.dtype == torch.float32 and x_nhwc.is_contiguous() and x_nhwc.dim() == 4
+    B, H, W, Cin = x_nhwc.shape
+    out = torch.empty((B, Ho, Wo, nout), dtype=torch.float32, device=x_nhwc.device)
+    p = GemmX3Params()
+    p.mode = X3_CONVT if transposed else X3_CONV
+    p.a1, p.ld1, p.k1 = _p(x_nhwc), Cin, Cin
+    p.a2, p.ld2, p.k2 = None, 0, 0
+    p.H, p.W, p.Ho, p.Wo, p.KH, p.KW, p.pad = H, W, int(Ho), int(Wo), int(KH), int(KW), int(pad)
+    p.M, p.K = B * Ho * Wo, KH * KW * Cin
+    p.w_hi, p.w_lo = _p(w_split[0]), _p(w_split[1])
+    p.bias, p.act, p.slope = _p(bias), int(bool(act)), float(slope)
+    p.out, p.ld_out, p.Nout = _p(out), int(nout), int(nout)
+    _gemm_x3(p, ("X3C", KH * KW * Cin, (int(nout),), OUT_F32, B * Ho * Wo, 0))
+    return out
+
+
+# ------------------------------------------------------------------------------------ fp32 SIMT path
 def linear_f32(a1, w, bias=None, act=False, slope=0.0, a2=None, out=None):
     """y = act([a1|a2] @ w.T + bias); a* are (..., K*) row-major views with unit inner stride."""
     _need_cuda(a1, w, bias, a2)

@@ -85,12 +85,38 @@ int cp_fold_edgeconv(const float* conv_w, const float* gamma, const float* beta,
 size_t cp_packed_weight_bytes(int Nout, int K);
 int cp_pack_weight(const float* w, int Nout, int K, void* packed, cp_stream_t s);
 
-/* ---- fp32 validation path (SIMT FFMA) -------------------------------------------------------
+/* ---- fp32 SIMT GEMM (FFMA): shapes the tensor-core kernel below does not take (K not a multiple of 64) ----
  * y[m, :] = act([a1[m, :K1] | a2[m, :K2]] . w^T + bias);  w (Nout, K1+K2) row-major;  a2 may be NULL.
  * act: 0 = none, 1 = LeakyReLU(slope).  Replaces nn.Linear(+LeakyReLU) (pipeline.py:61-69) and the
  * folded EdgeConv node GEMM. */
 int cp_linear_f32(const float* a1, int lda1, int K1, const float* a2, int lda2, int K2, const float* w,
                   const float* bias, int act, float slope, float* y, int ldy, int64_t M, int Nout, cp_stream_t s);
+
+/* ---- float32 mode on the tensor cores: split-bf16 x3 GEMM / implicit-GEMM convolution (tcgen05) ----
+ * out[m, :Nout] = act(A[m, :K] . W^T + bias) with every fp32 operand split on the fly into bf16 hi + lo and the
+ * product taken as hi.hi + hi.lo + lo.hi (fp32 accumulation in TMEM; ~2^-16 relative per product; fp32 in, fp32 out).
+ *   CP_X3_LINEAR : A[m] = [a1[m, :k1] | a2[m, :k2]]  (k1 + k2 == K; a2 may be NULL with k2 == 0) -- nn.Linear
+ *                  (+LeakyReLU) of pipeline.py:61-69, the folded EdgeConv node GEMM, the concat of pipeline.py:283.
+ *   CP_X3_CONV   : a1 = NHWC map (B, H, W, k1 = Cin); row m = output pixel (b, oy, ox) of a (B, Ho, Wo) grid;
+ *                  A[m, (ky*KW + kx)*Cin + c] = a1[b, oy - pad + ky, ox - pad + kx, c] (0 outside the map): Conv2d
+ *                  KH x KW, stride 1 (pipeline.py:144-145, 195-208).  W row n = weight[n] in (ky, kx, c) order.
+ *   CP_X3_CONVT  : the same gather for ConvTranspose2d stride 2 (pipeline.py:187-197): tap (ky, kx) reads
+ *                  a1[b, (oy + pad - ky) / 2, (ox + pad - kx) / 2, c] when both are even and inside the map.
+ * act: 0 = none, 1 = LeakyReLU(slope) (slope 0 = ReLU).  K, k1, k2 multiples of 64; weights packed by
+ * cp_pack_weight_split (two images of cp_pack_weight's layout: bf16(w) and bf16(w - bf16(w))). */
+enum { CP_X3_LINEAR = 0, CP_X3_CONV = 1, CP_X3_CONVT = 2 };
+typedef struct {
+  int mode;
+  const float* a1; int ld1; int k1;
+  const float* a2; int ld2; int k2;
+  int H, W, Ho, Wo, KH, KW, pad;
+  int64_t M; int K;
+  const void* w_hi; const void* w_lo;
+  const float* bias; int act; float slope;
+  float* out; int ld_out; int Nout;
+} cp_gemm_x3_params;
+int cp_pack_weight_split(const float* w, int Nout, int K, void* packed_hi, void* packed_lo, cp_stream_t s);
+int cp_gemm_x3(const cp_gemm_x3_params* p, cp_stream_t s);
 
 /* ---- K2: EdgeConv -----------------------------------------------------------------------------
  * Aggregation half:  y[b,i,c] = lrelu(max_k z[b, idx[g(b), i, k], c] + z[b, i, Co + c]),  z (B,N,2Co).

@@ -269,6 +269,60 @@ def test_correspondences_packed_roundtrip(cp):
     assert np.array_equal(x2, xid.cpu().numpy()) and np.array_equal(y2, yid.cpu().numpy()) and np.array_equal(bb, bbox.cpu().numpy())
 
 
+# ------------------------------------------------------------------------------------------------ split-bf16 x3 GEMM
+@pytest.mark.parametrize("M,K1,K2,Nout,act", [(300, 64, 0, 128, False), (1000, 256, 64, 256, True), (257, 256, 256, 512, True),
+                                               (128, 64, 0, 7, False), (513, 1024, 0, 600, False), (4096, 256, 0, 2, False)])
+def test_gemm_x3_linear_matches_fp64(cp, M, K1, K2, Nout, act):
+    """The float32-mode GEMM on tcgen05 (fp32 operands split into bf16 hi + lo, three MMAs) against float64: the
+    error budget is ~2^-16 per product, i.e. far inside north_star's 1e-3 and the 1e-4 logit band."""
+    ops = cp.ops
+    g = torch.Generator().manual_seed(M + K1 + Nout)
+    a1 = torch.randn(M, K1, generator=g)
+    a2 = torch.randn(M, K2, generator=g) if K2 else None
+    w = torch.randn(Nout, K1 + K2, generator=g) / (K1 + K2) ** 0.5
+    bias = torch.randn(Nout, generator=g)
+    a = a1 if a2 is None else torch.cat([a1, a2], dim=1)
+    ref = a.double() @ w.double().t() + bias.double()
+    if act:
+        ref = torch.where(ref > 0, ref, ref * 0.01)
+    ws = ops.pack_weight_split(w.cuda())
+    out = ops.gemm_x3_linear(a1.cuda(), ws, Nout, bias.cuda(), act, 0.01, a2=None if a2 is None else a2.cuda())
+    err = float((out.cpu().double() - ref).abs().max() / ref.abs().max())
+    fp32 = float(((a @ w.t() + bias).double() - (a.double() @ w.double().t() + bias.double())).abs().max() / ref.abs().max())
+    print(f"x3 GEMM M={M} K={K1}+{K2} N={Nout}: max err / max = {err:.2e} (plain fp32 matmul on the CPU: {fp32:.2e})")
+    assert out.shape == (M, Nout) and err < 2e-5, err
+    # rows beyond M / columns beyond Nout are never written
+    canvas = torch.full((M + 3, Nout + 5), float("nan"), device="cuda")
+    ops.gemm_x3_linear(a1.cuda(), ws, Nout, bias.cuda(), act, 0.01, a2=None if a2 is None else a2.cuda(), out=canvas[:M, :Nout])
+    assert torch.isnan(canvas[M:]).all() and torch.isnan(canvas[:, Nout:]).all() and torch.equal(canvas[:M, :Nout], out)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,k,pad,transposed", [(3, 16, 256, 256, 3, 1, False), (2, 32, 64, 64, 2, 1, False),
+                                                           (2, 8, 128, 64, 3, 1, True), (5, 9, 64, 2, 1, 0, False)])
+def test_gemm_x3_conv_matches_fp64(cp, B, H, Cin, Cout, k, pad, transposed):
+    """Implicit-GEMM convolution of the float32 mode against torch's float64 convolution on the CPU."""
+    import torch.nn.functional as F
+    ops = cp.ops
+    g = torch.Generator().manual_seed(B + H + Cin + k)
+    x = torch.randn(B, Cin, H, H, generator=g)
+    bias = torch.randn(Cout, generator=g)
+    if transposed:
+        w = torch.randn(Cin, Cout, k, k, generator=g) / (Cin * k * k / 4) ** 0.5
+        ref = F.conv_transpose2d(x.double(), w.double(), bias.double(), stride=2, padding=pad, output_padding=1)
+        wm = w.permute(1, 2, 3, 0).reshape(Cout, k * k * Cin)
+    else:
+        w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+        ref = F.conv2d(x.double(), w.double(), bias.double(), stride=1, padding=pad)
+        wm = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)
+    ref = torch.relu(ref)
+    Ho = ref.shape[2]
+    ws = ops.pack_weight_split(wm.contiguous().cuda())
+    out = ops.gemm_x3_conv(x.permute(0, 2, 3, 1).contiguous().cuda(), ws, Cout, k, k, pad, Ho, Ho, bias.cuda(), True, 0.0, transposed)
+    err = float((out.cpu().double().permute(0, 3, 1, 2) - ref).abs().max() / ref.abs().max())
+    print(f"x3 conv {'T' if transposed else ''} B={B} H={H} {Cin}->{Cout} k={k}: max err / max = {err:.2e}")
+    assert out.shape == (B, Ho, Ho, Cout) and err < 2e-5, err
+
+
 # ------------------------------------------------------------------------------------------------ tcgen05 chain
 def _bf16_round(t):
     return t.to(torch.bfloat16).float()

@@ -54,6 +54,18 @@ int make_out_tensor_map(void* map128, void* out, int ncols, int ld_out, int N, i
   CP_REQUIRE(r == CUDA_SUCCESS, CP_E_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r);
   return CP_OK;
 }
+int make_f32_tensor_map_2d(void* map128, void* out, int64_t ncols, int64_t nrows, int64_t ld, const char* who) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  CP_REQUIRE(enc, CP_E_CUDA, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
+  const cuuint64_t dims[2] = {(cuuint64_t)ncols, (cuuint64_t)nrows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  const CUresult r = enc(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CP_REQUIRE(r == CUDA_SUCCESS, CP_E_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r);
+  return CP_OK;
+}
 }  // namespace cp
 
 extern "C" const char* cp_last_error_string(void) { return cp::g_err; }

@@ -246,6 +246,8 @@ def edgeconv_node_major(sg_module, x_nm, ctx: GraphCtx, dtype):
     B, N, C = x_nm.shape
     if dtype == torch.float32:
         z = linear32(x_nm, prep)
+        if ctx.plan.struct is not None and ctx.plan.max_unique <= ops.PLAN_UMAX and prep.Co % 32 == 0:
+            return ops.edge_aggregate_staged(z, ctx.plan, ctx.sel, prep.slope)     # rows staged in shared memory per tile
         return ops.edge_aggregate(z, ctx.plan.idx_p, ctx.sel, prep.slope)
     if not (_chain_ok(C) and _chain_ok(prep.Co)):
         raise RuntimeError(f"bf16 EdgeConv supports C, C' in {{64,128,256}} (got {C}->{prep.Co}); use float32 mode")
@@ -468,11 +470,15 @@ class _X3Seq:
                 ok = (m.groups == 1 and tuple(m.dilation) == (1, 1) and m.padding[0] == m.padding[1] and
                       (tuple(m.stride) == ((2, 2) if tr else (1, 1))) and (not tr or tuple(m.output_padding) == (1, 1)))
                 cin, cout = (w.shape[0], w.shape[1]) if tr else (w.shape[1], w.shape[0])
-                if not ok or cin % 64 != 0:
+                if not ok:
                     raise RuntimeError(f"float32 image branch: unsupported convolution {m}")
-                wm = (w.permute(1, 2, 3, 0) if tr else w.permute(0, 2, 3, 1)).reshape(cout, kh * kw * cin).contiguous()
+                wk = w.permute(1, 2, 3, 0) if tr else w.permute(0, 2, 3, 1)        # (cout, kh, kw, cin)
+                cin_pad = (cin + 63) // 64 * 64                                      # the kernel's K chunks are 64 channels
+                if cin_pad != cin:
+                    wk = F.pad(wk, (0, cin_pad - cin))
+                wm = wk.reshape(cout, kh * kw * cin_pad).contiguous()
                 self.ops.append(("convT" if tr else "conv", ops.pack_weight_split(wm), None if b is None else b.contiguous(),
-                                 (cout, kh, kw, int(m.padding[0])), relu))
+                                 (cout, kh, kw, int(m.padding[0]), cin_pad), relu))
             elif isinstance(m, nn.UpsamplingBilinear2d):
                 if float(m.scale_factor) != 2.0:
                     raise RuntimeError("image branch: only UpsamplingBilinear2d(scale_factor=2) is supported")
@@ -505,7 +511,9 @@ class _X3Seq:
             y = self._nhwc(x)
         for kind, ws, b, geom, relu in self.ops[start:]:
             if kind in ("conv", "convT"):
-                cout, kh, kw, pad = geom
+                cout, kh, kw, pad, cin_pad = geom
+                if y.shape[-1] != cin_pad:                    # zero channels up to the kernel's 64-channel granularity
+                    y = F.pad(y, (0, cin_pad - y.shape[-1]))
                 H, W = y.shape[1], y.shape[2]
                 if kind == "conv":
                     Ho, Wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1

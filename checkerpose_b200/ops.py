@@ -302,6 +302,20 @@ def edge_aggregate(z, idx32, graph_sel, slope, out=None):
     return out
 
 
+def edge_aggregate_staged(z, plan, graph_sel, slope, out=None):
+    """float32 aggregation on the graph plan (cp_edge_aggregate_staged_f32): z (B,N,2Co) fp32 in PLAN order -> (B,N,Co)."""
+    _need_cuda(z, graph_sel)
+    B, N, C2 = z.shape
+    Co = C2 // 2
+    assert z.dtype == torch.float32 and z.is_contiguous() and N == plan.N
+    if out is None:
+        out = torch.empty((B, N, Co), dtype=torch.float32, device=z.device)
+    check(lib.cp_edge_aggregate_staged_f32(_p(z), C.byref(plan.struct), _p(graph_sel), float(slope), _p(out), B, N, Co, _stream()),
+          "cp_edge_aggregate_staged_f32")
+    _count()
+    return out
+
+
 def sample_taps(patches_nhwc, x_id, y_id, mask, tap_step, out=None):
     """patches (B,Hp,Wp,E) contiguous, ids (B,N) int64, mask (B,N) f32|None -> (B,N,4E)."""
     _need_cuda(patches_nhwc, x_id, y_id, mask)

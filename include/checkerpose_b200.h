@@ -205,6 +205,13 @@ typedef struct { /* DEVICE pointers to the arrays cp_graph_plan_build produced *
   const uint16_t* prog;
 } cp_graph_plan;
 
+/* float32 aggregation half of the factored EdgeConv on the graph plan: y (B,N,Co) fp32 = lrelu(max_k P[nbr] + Q),
+ * z (B,N,2Co) fp32 = [P|Q], both in PLAN order.  Stages every tile's distinct neighbour rows in shared memory once per
+ * 32-channel slice and reduces the plan's node pairs (the float32 mode's counterpart of cp_edgeconv_fwd's aggregators).
+ * Co % 32 == 0; every tile's distinct-row count <= CP_PLAN_UMAX (else use cp_edge_aggregate). */
+int cp_edge_aggregate_staged_f32(const float* z, const cp_graph_plan* plan, const int32_t* graph_sel, float slope, float* y,
+                                 int B, int N, int Co, cp_stream_t s);
+
 /* StaticGraph_module (pipeline.py:45-59) in the factored form, fused with the GEMM that consumes it:
  *   A[i,:]  = lrelu(max_k z[b, nbr(i,k), :Co] + z[b, i, Co:2Co])       (never leaves the SM)
  *   out     = act(A . W^T + bias)                                       (tcgen05, fp32 accumulate in TMEM)

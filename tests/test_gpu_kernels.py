@@ -113,6 +113,23 @@ def test_static_graph_module_fp32(cp, golden, tag):
     assert torch.allclose(y.cpu(), t("lm_y"), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("ds,objs,N,K,Co,B", [("lmo", (1,), 4096, 20, 256, 3), ("lm", (3, 7), 300, 20, 64, 4), ("ycbv", (5,), 1000, 8, 96, 2),
+                                               ("lmo", (5,), 512, 40, 32, 2)])
+def test_edge_aggregate_staged_f32_bit_exact(cp, ds, objs, N, K, Co, B):
+    """float32 aggregation on the graph plan (rows staged per tile, node pairs) == the unstaged gather kernel, bit for bit
+    (max and one add per element: no rounding freedom), incl. ragged last tiles and per-RoI graphs."""
+    ops = cp.ops
+    p3d = torch.cat([syn.p3d_normed_tensor(syn.load_fps_xyz(ds, o, N)) for o in objs], dim=0).cuda()
+    _, idx32 = ops.knn(p3d, K, want_i32=True)
+    plan = ops.GraphPlan(idx32, p3d)
+    g = torch.Generator().manual_seed(N + K + Co)
+    z = torch.randn(B, N, 2 * Co, generator=g).cuda()
+    sel = None if len(objs) == 1 else torch.randint(0, len(objs), (B,), generator=g).to(torch.int32).cuda()
+    want = ops.edge_aggregate(z, plan.idx_p, sel, 0.2)
+    got = ops.edge_aggregate_staged(z, plan, sel, 0.2)
+    assert torch.equal(got, want)
+
+
 def test_static_graph_requires_eval_and_cuda(cp, golden):
     g = golden("modules")
     m, t = _sg_module(cp, g, "a", lm=False)
@@ -157,7 +174,9 @@ def test_index2feat(cp, golden, tag, k, fd, ed):
     y = m(t("feat").cuda(), None, t("xid").cuda(), t("yid").cuda())
     assert y.shape == t("y").shape
     # the gather itself is an exact copy; the conv before it is cuDNN fp32 (not bit-identical to the CPU conv)
-    assert torch.allclose(y.cpu(), t("y"), rtol=1e-4, atol=1e-5)
+    # the patch convolution runs on the split-bf16 tensor-core GEMM (~2^-16 relative per product): north_star's fp32 bar
+    # is 1e-3 relative; held here to 1e-4 of the tensor's scale
+    assert torch.allclose(y.cpu(), t("y"), rtol=1e-4, atol=1e-4 * float(t("y").abs().max()))
     patches = cp.head.patches_nhwc(m.patch_generator, t("feat").cuda(), torch.float32)
     taps = cp.ops.sample_taps(patches, t("xid").cuda(), t("yid").cuda(), None, k)
     B, N = t("xid").shape
@@ -293,6 +312,11 @@ def test_gemm_x3_linear_matches_fp64(cp, M, K1, K2, Nout, act):
     assert out.shape == (M, Nout) and err < 2e-5, err
     # rows beyond M / columns beyond Nout are never written
     canvas = torch.full((M + 3, Nout + 5), float("nan"), device="cuda")
+    ops.gemm_x3_linear(a1.cuda(), ws, Nout, bias.cuda(), act, 0.01, a2=None if a2 is None else a2.cuda(), out=canvas[:M, :Nout])
+    assert torch.isnan(canvas[M:]).all() and torch.isnan(canvas[:, Nout:]).all() and torch.equal(canvas[:M, :Nout], out)
+    # the same through the TMA-store epilogue (16-byte aligned rows): the tensor map clips the ragged last tile
+    wide = (Nout + 3) // 4 * 4 + 8
+    canvas = torch.full((M + 3, wide), float("nan"), device="cuda")
     ops.gemm_x3_linear(a1.cuda(), ws, Nout, bias.cuda(), act, 0.01, a2=None if a2 is None else a2.cuda(), out=canvas[:M, :Nout])
     assert torch.isnan(canvas[M:]).all() and torch.isnan(canvas[:, Nout:]).all() and torch.equal(canvas[:M, :Nout], out)
 

@@ -539,3 +539,39 @@ def test_out_of_range_object_id_traps_instead_of_reading_out_of_bounds():
             "ops.graph_sel(torch.tensor([1, 16], device='cuda'), 15); torch.cuda.synchronize(); print('NOT TRAPPED')" % REPO)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert "valid ok" in r.stdout and "NOT TRAPPED" not in r.stdout and r.returncode != 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cuda_graph_capture_replays_the_head(dtype):
+    """the whole head is capturable in one CUDA graph (no host synchronisation, caller-owned
+    buffers, launches on the current stream) and a replay on NEW inputs equals the eager forward on them."""
+    from checkerpose_b200 import head, ops
+    from checkerpose_b200.graphs import CapturedHead
+    name = "head_ycbv21_n128_b2"
+    ds, objs, N, B, seed, lm = HEAD_CASES[name]
+    p3d, sd, feats, _ = head_case_inputs(name)
+    g = torch.Generator().manual_seed(5)
+    feats2 = [f.cuda() for f in syn.synthetic_features(B, g)]
+    bbox = syn.synthetic_bboxes(B, g).cuda()
+    net = build_net(N, p3d, False, sd)
+    head.set_compute_dtype(dtype)
+    try:
+        fdev = [f.cuda().to(dtype)[:, :, :, :] for f in feats]
+        cap = CapturedHead(net, fdev[1:], p3d.cuda().expand(B, -1, -1), bbox, packed=True)
+        n0 = ops.launch_count
+        out_g, rec_g = cap([f.to(dtype) for f in feats2[1:]], bbox)
+        assert ops.launch_count == n0, "a replay issues no launches through the Python wrappers"
+        out_g = [t.clone() for t in out_g]
+        rec_g = rec_g.clone()
+        out_e, rec_e = net.forward_with_correspondences([f.to(dtype) for f in feats2[1:]], p3d.cuda().expand(B, -1, -1), bbox, packed=True)
+    finally:
+        head.set_compute_dtype(torch.float32)
+    for a, b in zip(out_g, out_e):
+        if dtype == torch.float32:
+            assert torch.equal(a, b)          # no library kernels in float32 mode: bit-identical
+        elif a.dtype == torch.int64:
+            assert (a == b).float().mean() > 0.98
+        else:
+            assert (a - b).abs().max() <= 0.15 * b.abs().max()
+    if dtype == torch.float32:
+        assert torch.equal(rec_g, rec_e)

@@ -375,6 +375,7 @@ __device__ void stager(const EcParams& kp, uint8_t* sm, Bars* bars, int pw, int 
       }
       if (tid == 0) TR(5, r * 2 + 0);
       sts32(vs + (r % NBAR) * 4, nvh);
+      __syncwarp();      // every lane stores the same value and reads it back later: order the lanes explicitly (racecheck)
       vh = nvh + U;
       ph = nph + U;
       const uint32_t dst = sm_base + OFF_RING + (nph + q) * 128u + sub * 16;

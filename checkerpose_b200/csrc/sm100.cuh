@@ -135,6 +135,65 @@ __device__ __forceinline__ void mma_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, u
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
       : "memory");
 }
+// ---- CTA pairs (cta_group::2): one MMA over two SMs, issued by the leader CTA (cluster rank 0) ---------------
+// The pair protocol is the one CUTLASS' 2-SM kernels use: both CTAs keep identical shared-memory layouts; an MMA of
+// M = 256 takes rows [0,128) of A and rows [0, N/2) of B from the leader's shared memory and the other halves from the
+// peer's at the SAME offsets; each CTA's TMEM holds the accumulator rows of its own A half.  Barriers the leader's MMA
+// thread waits on live in the leader's shared memory; the peer arrives on them through the cluster address of rank 0
+// (mapa), and tcgen05.commit.multicast::cluster releases buffers in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // release at cluster scope
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar_s, uint32_t parity) {   // acquire at cluster scope
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar_s), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem, uint32_t ncols) {  // one warp in EACH CTA, same warp id
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=m (128 per CTA of a pair: m = 256), N=n.
+__device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void mma2_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
+// arrive (when all tcgen05 ops issued so far by this thread have completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void mma2_commit_both(uint32_t bar_s) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_s), "h"((uint16_t)3) : "memory");
+}
+
 // Arrive on an mbarrier when all tcgen05 ops issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

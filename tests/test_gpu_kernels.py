@@ -489,6 +489,37 @@ def _fixture_plan(cp, ds, objs, N, K):
     return plan
 
 
+@pytest.mark.parametrize("N,B,nout", [(4096, 3, 512), (300, 5, 256), (512, 2, 16), (640, 1, 128)])
+def test_edgeconv_cta_pair_matches_single_cta(cp, monkeypatch, N, B, nout):
+    """The CTA-pair variant of the staged EdgeConv kernel (cluster of 2, tcgen05.mma.cta_group::2, M = 256: opt-in with
+    CP_EDGECONV_PAIR=1) equals the single-CTA kernel bit for bit, incl. odd tile counts (the last pair repeats a tile),
+    ragged last tiles, and outputs of 16 / 128 / 256 / 512 columns."""
+    ops = cp.ops
+    C = 256 if nout != 128 else 64
+    if nout == 16:
+        C = 64
+    p3d = syn.p3d_normed_tensor(syn.load_fps_xyz("lmo", 1, N)).cuda()
+    _, idx32 = ops.knn(p3d, 20, want_i32=True)
+    plan = ops.GraphPlan(idx32, p3d)
+    g = torch.Generator().manual_seed(N + nout)
+    z = torch.randn(B, N, 2 * C, generator=g).to(torch.bfloat16).cuda()
+    w = torch.randn(nout, C, generator=g) / C ** 0.5
+    bias = torch.randn(nout, generator=g).cuda()
+    layer = ops.chain_layer(ops.pack_weight(w.cuda()), bias, C, nout, nout != 16, 0.01)
+    outs = []
+    for pair in ("0", "1"):
+        monkeypatch.setenv("CP_EDGECONV_PAIR", pair)
+        if nout == 16:
+            out = torch.zeros((B, N, 16), dtype=torch.float32, device="cuda")
+            ops.edgeconv_fwd(z=z, plan=plan, graph_sel=None, agg_slope=0.2, layer=layer, out=out, out_mode=ops.OUT_F32, n_valid=7)
+        else:
+            out = torch.zeros((B, N, nout), dtype=torch.bfloat16, device="cuda")
+            ops.edgeconv_fwd(z=z, plan=plan, graph_sel=None, agg_slope=0.2, layer=layer, out=out, out_mode=ops.OUT_BF16)
+        outs.append(out.clone())
+    assert torch.isfinite(outs[0].float()).all() and float(outs[0].float().abs().sum()) > 0
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("ds,objs,N,K,Co,Nout,B,out_f32", [
     ("lmo", (1,), 512, 20, 256, 512, 3, False),      # refine-layer shape
     ("ycbv", (21,), 300, 20, 64, 128, 2, False),     # init-layer shape, ragged last tile

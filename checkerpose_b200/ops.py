@@ -601,6 +601,34 @@ def unpack_correspondences_host(packed, S: int = 64):
     return np.stack([u, v], axis=-1).astype(np.float32), flags, x_id, y_id, bbox
 
 
+FLAG_ALL, FLAG_FULL, FLAG_VISIB = 1, 2, 4
+
+
+def pnp_ransac(packed, p3d_xyz, cam_K, graph_sel=None, flag=FLAG_ALL, reproj_thresh=2.0, iterations=150, seed=0,
+               return_inlier_mask=False, S=64):
+    """Batched RANSAC PnP over correspondence records (cp_pnp_ransac): ``packed`` is either the (B, 16 + 2N) uint8 rows of
+    ``correspondences_packed`` or the (B,N,3) int32 records of ``correspondences``; p3d_xyz (G,N,3) f32 object keypoints in mm,
+    cam_K (3,3) or (B,3,3) -> (R (B,3,3) f32, t (B,3) f32, inlier count (B) int32[, mask (B,N) u8])."""
+    _need_cuda(packed, p3d_xyz, cam_K, graph_sel)
+    assert packed.is_contiguous()
+    B = packed.shape[0]
+    is_packed = packed.dtype == torch.uint8
+    N = (packed.shape[1] - 16) // 2 if is_packed else packed.shape[1]
+    p3d = p3d_xyz.reshape(-1, N, 3).contiguous().float()
+    Kc = cam_K.reshape(-1, 9).contiguous().float()
+    if Kc.shape[0] not in (1, B):
+        raise RuntimeError("pnp_ransac: cam_K must be (3,3) or (B,3,3)")
+    pose = torch.empty((B, 12), dtype=torch.float32, device=packed.device)
+    ninl = torch.empty((B,), dtype=torch.int32, device=packed.device)
+    mask = torch.empty((B, N), dtype=torch.uint8, device=packed.device) if return_inlier_mask else None
+    check(lib.cp_pnp_ransac(_p(packed if is_packed else None), _p(None if is_packed else packed), _p(p3d), _p(graph_sel), _p(Kc), int(Kc.shape[0] == B and B > 1), int(flag), float(reproj_thresh),
+                            int(iterations), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(pose), _p(ninl), _p(mask), B, N, int(S), _stream()),
+          "cp_pnp_ransac")
+    _count()
+    R, t = pose[:, :9].reshape(B, 3, 3), pose[:, 9:]
+    return (R, t, ninl, mask) if return_inlier_mask else (R, t, ninl)
+
+
 def split_correspondences(rec: torch.Tensor):
     """(…,3) int32 records -> (uv float32 (…,2), flags int32 (…))."""
     uv = rec[..., :2].contiguous().view(torch.float32)

@@ -291,6 +291,21 @@ int cp_correspondences_pack(const float* roi_bit, const float* seg, const float*
                             const int64_t* y_id, uint8_t* out, int B, int N, int S, cp_stream_t s);
 int cp_correspondences_unpack(const uint8_t* packed, cp_corr_record* out, int B, int N, int S, cp_stream_t s);
 
+/* ---- batched RANSAC PnP over the packed records -----------------------------------------
+ * Second half of from_id_to_pose (test_network_with_test_data.py:97-115), where the reference calls
+ * cv2.solvePnPRansac(valid_p3d, valid_p2d, cam_K, None, reprojectionError, iterationsCount, flags=SOLVEPNP_EPNP) per RoI
+ * on the CPU.  One CTA per RoI: valid correspondences (record flags & flag_mask: 1 = roi bit, 2 = & full mask, 4 = &
+ * visible mask) -> `iterations` (rounded up to a multiple of 256) P3P hypotheses scored against all of them -> Gauss-Newton
+ * refit on the inliers.  Exactly one of: packed (B, 16 + 2N) rows of cp_correspondences_pack, records (B, N) 12-byte records
+ * of cp_correspondences.  p3d (G, N, 3) f32 object keypoints (mm) in
+ * keypoint order; graph_sel (B) int32 or NULL; cam_K (B, 9) f32 row-major if k_batched else (9).
+ * pose_out (B, 12) f32 = R row-major (9) | t (3) with x_cam = R x_obj + t; ninl_out (B) int32 inlier count;
+ * inlier_mask_out (B, N) u8 or NULL.  Fewer than 4 valid correspondences give R = I, t = 0, 0 inliers (reference :111-114).
+ * Deterministic for a given seed.  Not a port of OpenCV: parity is agreement of the estimated pose (tests/test_gpu_pnp.py). */
+int cp_pnp_ransac(const uint8_t* packed, const cp_corr_record* records, const float* p3d, const int32_t* graph_sel, const float* cam_K, int k_batched,
+                  int flag_mask, float reproj_thresh, int iterations, uint64_t seed, float* pose_out, int32_t* ninl_out,
+                  uint8_t* inlier_mask_out, int B, int N, int S, cp_stream_t s);
+
 /* Elementwise helpers behind common_ops.py:5-27 and pipeline.py:84-127.
  * out = sigmoid(x) > thr ? 1 : 0 as f32 (out_dtype 0) or int64 (out_dtype 1). */
 int cp_threshold(const float* x, float thr, int apply_sigmoid, void* out, int out_dtype, int64_t count, cp_stream_t s);

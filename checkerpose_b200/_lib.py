@@ -61,6 +61,19 @@ class GemmX3Params(C.Structure):
     ]
 
 
+class QueryDecodeParams(C.Structure):
+    _fields_ = [
+        ("B", c_i32), ("N", c_i32),
+        ("src", c_vp), ("ld_src", c_i32), ("kin", c_i32),
+        ("w1_packed", c_vp), ("b1", c_vp), ("nmid", c_i32), ("slope", c_f32),
+        ("w2", c_vp), ("b2", c_vp), ("nout", c_i32),
+        ("logits", c_vp), ("ld_logits", c_i32),
+        ("plane", c_i32), ("Ltot", c_i32),
+        ("x_bits", c_vp), ("y_bits", c_vp), ("x_id", c_vp), ("y_id", c_vp), ("x_id_kp", c_vp), ("y_id_kp", c_vp),
+        ("perm", c_vp), ("graph_sel", c_vp),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol of include/checkerpose_b200.h
 SIGNATURES = {
     "cp_last_error_string": (C.c_char_p, []),
@@ -70,6 +83,7 @@ SIGNATURES = {
     "cp_gemm_x3": (c_i32, [C.POINTER(GemmX3Params), c_vp]),
     "cp_edge_aggregate_staged_f32": (c_i32, [c_vp, C.POINTER(GraphPlanStruct), c_vp, c_f32, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cp_pnp_ransac": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, C.c_uint64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "cp_query_decode_fwd": (c_i32, [C.POINTER(QueryDecodeParams), c_vp]),
     "cp_graph_sel": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "cp_knn": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp_transpose_cn_to_nc": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

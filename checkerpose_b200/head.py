@@ -576,10 +576,13 @@ def patches_nhwc(patch_generator, img_feat, dtype):
 # --------------------------------------------------------------------------------------------------
 # refine stage (Refine_moduleGNN.forward, pipeline.py:262-298)
 # --------------------------------------------------------------------------------------------------
-def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, ctx, dtype):
+def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, ctx, dtype, decode=None):
     """One refine stage on plan-order node tensors: gfeat_nm (B,N,Cg) of ``dtype``, roi_mask (B,N) f32 {0,1}, ids (B,N)
     int64, ctx = graph_ctx of the stage's graph (None when it has no graph modules).
-    -> logits (B,N,>=2) f32 [x_new, y_new], graph feature (B,N,C) of ``dtype``."""
+    -> logits (B,N,>=2) f32 [x_new, y_new], graph feature (B,N,C) of ``dtype``.
+    ``decode`` = dict(plane, Ltot, x_bits, y_bits, perm, sel[, x_id_kp, y_id_kp]): in bf16 mode the stage's tail (query layers 2
+    and 3 + the decode of pipeline.py:375-381, ids updated IN PLACE) runs as one launch (cp_query_decode_fwd) and the returned
+    logits are None."""
     _require_eval(ref)
     B, N, Cg = gfeat_nm.shape
     dev = gfeat_nm.device
@@ -641,6 +644,11 @@ def refine_node_major(ref, img_feat, gfeat_nm, roi_mask, x_id, y_id, ctx, dtype)
     feat = torch.empty((B, N, preps[-1].Co), dtype=torch.bfloat16, device=dev)
     hq = torch.empty((B, N, q[0].nout), dtype=torch.bfloat16, device=dev)
     _agg_gemm(z, ctx, preps[-1].slope, q_layers[0], hq, ops.OUT_BF16, a_out=feat)
+    if decode is not None and q[1].nout == 64 and q[2].nout == 2 and q[1].kin in (64, 128, 256):
+        ops.query_decode_fwd(src=hq, w1_packed=q[1].packed, b1=q[1].b, slope=qslope, w2=q[2].w, b2=q[2].b, plane=decode["plane"],
+                             Ltot=decode["Ltot"], x_bits=decode["x_bits"], y_bits=decode["y_bits"], x_id=x_id, y_id=y_id,
+                             perm=decode["perm"], graph_sel=decode["sel"], x_id_kp=decode.get("x_id_kp"), y_id_kp=decode.get("y_id_kp"))
+        return None, feat
     ops.chain_fwd(**common, prologue=ops.PRO_LOAD, src=hq, layers=q_layers[1:], out=logits, out_mode=ops.OUT_F32,
                   n_valid=q[2].nout)
     return logits, feat
@@ -776,13 +784,14 @@ def pose_head_forward(net, img_feats, obj_ids=None, stage=None, dtype=None, bbox
     for i in range(nact):
         img_feat = image_block(net.up_net[i], img_feat, dtype, skip=img_feats[-i - 1] if i > 0 else None)
         ctx = _stage_ctx(net, net.refine_net[i], obj_ids, B, dev, ctx0)
-        logits, gfeat = refine_node_major(net.refine_net[i], img_feat, gfeat, roi_mask, x_id, y_id, ctx, dtype)
-        if perm is not None and i == nact - 1:   # last stage: the ids the caller sees, in keypoint order
-            x_kp, y_kp = torch.empty_like(x_id), torch.empty_like(y_id)
+        last_kp = perm is not None and i == nact - 1     # last stage: the ids the caller sees, in keypoint order
+        x_kp, y_kp = (torch.empty_like(x_id), torch.empty_like(y_id)) if last_kp else (None, None)
+        decode = dict(plane=L0 + i, Ltot=Ltot, x_bits=x_bits, y_bits=y_bits, perm=perm, sel=sel, x_id_kp=x_kp, y_id_kp=y_kp)
+        logits, gfeat = refine_node_major(net.refine_net[i], img_feat, gfeat, roi_mask, x_id, y_id, ctx, dtype, decode=decode)
+        if logits is not None:      # the stage's tail did not fuse the decode (float32 mode, unusual query dims)
             ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id, perm, sel, x_kp, y_kp)
+        if last_kp:
             x_id, y_id = x_kp, y_kp
-        else:
-            ops.decode_refine(logits, L0 + i, Ltot, x_bits, y_bits, x_id, y_id, perm, sel)
     if perm is not None and nact == 0:
         x_id = ops.permute_rows(x_id.view(B, N, 1), perm, sel, True).view(B, N)
         y_id = ops.permute_rows(y_id.view(B, N, 1), perm, sel, True).view(B, N)

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ChainLayer, ChainParams, EdgeConvParams, GemmX3Params, GraphPlanStruct, check, lib
+from ._lib import ChainLayer, ChainParams, EdgeConvParams, GemmX3Params, GraphPlanStruct, QueryDecodeParams, check, lib
 
 CP_F32, CP_BF16 = 0, 1
 PRO_LOAD, PRO_AGG, PRO_TAPS = 0, 1, 2
@@ -522,6 +522,33 @@ def decode_refine(logits, plane, Ltot, x_bits, y_bits, x_id, y_id, perm=None, gr
     B, N = x_id.shape
     check(lib.cp_decode_refine(_p(logits), logits.shape[-1], plane, Ltot, _p(x_bits), _p(y_bits), _p(x_id), _p(y_id),
                                _p(x_id_kp), _p(y_id_kp), B, N, _p(perm), _p(graph_sel), _stream()), "cp_decode_refine")
+    _count()
+
+
+def query_decode_fwd(*, src, w1_packed, b1, slope, w2, b2, plane, Ltot, x_bits, y_bits, x_id, y_id, perm=None, graph_sel=None,
+                     x_id_kp=None, y_id_kp=None, logits=None):
+    """Fused tail of a refine stage (cp_query_decode_fwd): src (B,N,kin) bf16 -> lrelu(Linear kin->64) -> Linear 64->2 -> the
+    decode of decode_refine (bit planes, id = 2 id + bit in place, keypoint-order ids).  One launch, TMA tensor loads."""
+    _need_cuda(src, w1_packed, b1, w2, b2, x_bits, y_bits, x_id, y_id, perm, graph_sel, x_id_kp, y_id_kp, logits)
+    assert src.dtype == torch.bfloat16 and src.stride(-1) == 1 and w2.dtype == torch.float32 and w2.is_contiguous() and tuple(w2.shape) == (2, 64)
+    B, N, kin = src.shape
+    p = QueryDecodeParams()
+    p.B, p.N = B, N
+    p.src, p.ld_src, p.kin = _p(src), src.stride(-2), kin
+    p.w1_packed, p.b1, p.nmid, p.slope = _p(w1_packed), _p(b1), 64, float(slope)
+    p.w2, p.b2, p.nout = _p(w2), _p(b2), 2
+    p.logits, p.ld_logits = _p(logits), (0 if logits is None else logits.shape[-1])
+    p.plane, p.Ltot = int(plane), int(Ltot)
+    p.x_bits, p.y_bits, p.x_id, p.y_id, p.x_id_kp, p.y_id_kp = _p(x_bits), _p(y_bits), _p(x_id), _p(y_id), _p(x_id_kp), _p(y_id_kp)
+    p.perm, p.graph_sel = _p(perm), _p(graph_sel)
+    if chain_event_log is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.cp_query_decode_fwd(C.byref(p), _stream()), "cp_query_decode_fwd")
+        e1.record()
+        chain_event_log.append((("QT", kin, (64, 2), OUT_F32, B, N), e0, e1))
+    else:
+        check(lib.cp_query_decode_fwd(C.byref(p), _stream()), "cp_query_decode_fwd")
     _count()
 
 

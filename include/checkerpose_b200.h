@@ -271,6 +271,24 @@ int cp_decode_init(const float* logits, int ld, int L, int Ltot, float* roi_bit,
 int cp_decode_refine(const float* logits, int ld, int plane, int Ltot, float* x_bits, float* y_bits,
                      int64_t* x_id, int64_t* y_id, int64_t* x_id_kp, int64_t* y_id_kp, int B, int N,
                      const int32_t* perm, const int32_t* graph_sel, cp_stream_t s);
+
+/* ---- K4 fused: tail of a refine stage = query MLP layers 2 and 3 + decode_refine, one launch (query_tail_tcgen05.cu) ----
+ * src (B*N, kin) bf16 plan-order rows = lrelu(W_q0 h + b_q0) (the first query layer is fused into the last EdgeConv launch);
+ *   hid   = lrelu(src . W1^T + b1)      kin -> 64      tcgen05, A tiles by TMA tensor loads      (MLP_QueryNet, pipeline.py:174-180)
+ *   [x,y] = hid . W2^T + b2             64 -> 2        fp32 register dot products
+ * then exactly cp_decode_refine on [x, y] (pipeline.py:375-381).  logits (B*N, ld_logits) f32 may be NULL.
+ * kin in {64, 128, 256}; nmid == 64; nout == 2; w1_packed from cp_pack_weight; w2 (2, 64) f32 row-major. */
+typedef struct {
+  int B, N;
+  const void* src; int ld_src; int kin;
+  const void* w1_packed; const float* b1; int nmid; float slope;
+  const float* w2; const float* b2; int nout;
+  float* logits; int ld_logits;
+  int plane, Ltot;
+  float* x_bits; float* y_bits; int64_t* x_id; int64_t* y_id; int64_t* x_id_kp; int64_t* y_id_kp;
+  const int32_t* perm; const int32_t* graph_sel;
+} cp_query_decode_params;
+int cp_query_decode_fwd(const cp_query_decode_params* p, cp_stream_t s);
 /* Plan order <-> keypoint order for node-major rows of row_bytes bytes (multiple of 4), out of place:
  * to_keypoint_order != 0: dst[b, perm[g(b)][n], :] = src[b, n, :];  == 0: dst[b, n, :] = src[b, perm[g(b)][n], :]. */
 int cp_permute_rows(const void* src, void* dst, int row_bytes, int B, int N, const int32_t* perm,

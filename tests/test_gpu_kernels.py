@@ -288,6 +288,52 @@ def test_correspondences_packed_roundtrip(cp):
     assert np.array_equal(x2, xid.cpu().numpy()) and np.array_equal(y2, yid.cpu().numpy()) and np.array_equal(bb, bbox.cpu().numpy())
 
 
+# ------------------------------------------------------------------------------------------------ fused query tail + decode (K4)
+@pytest.mark.parametrize("N,B,kin,with_kp", [(4096, 3, 256, True), (300, 2, 256, False), (512, 4, 64, True)])
+def test_query_decode_fused(cp, N, B, kin, with_kp):
+    """cp_query_decode_fwd (TMA tensor loads -> tcgen05 kin->64 -> fp32 64->2 -> decode) against float64 maths on the same
+    bf16-rounded operands: logits to 1e-3 of scale; bit planes, in-place id update and keypoint-order ids exactly the decode of
+    those logits (pipeline.py:375-381), scattered through the plan permutation of a per-RoI graph selection."""
+    ops = cp.ops
+    g = torch.Generator().manual_seed(N + kin)
+    src = torch.randn(B, N, kin, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(64, kin, generator=g) / kin ** 0.5).to(torch.bfloat16).float()
+    b1 = torch.randn(64, generator=g) * 0.1
+    w2 = torch.randn(2, 64, generator=g) / 8.0
+    b2 = torch.randn(2, generator=g) * 0.1
+    G, Ltot, plane = 2, 6, 4
+    perm = torch.stack([torch.randperm(N, generator=g) for _ in range(G)]).to(torch.int32)
+    sel = torch.randint(0, G, (B,), generator=g).to(torch.int32)
+    x_id0 = torch.randint(0, 16, (B, N), generator=g)
+    y_id0 = torch.randint(0, 16, (B, N), generator=g)
+    hid = src.double() @ w1.double().t() + b1.double()
+    hid = torch.where(hid > 0, hid, hid * 0.01)
+    ref = hid @ w2.double().t() + b2.double()                              # (B,N,2)
+    x_bits = torch.full((B, Ltot, N), float("nan")).cuda()
+    y_bits = torch.full((B, Ltot, N), float("nan")).cuda()
+    x_id, y_id = x_id0.clone().cuda(), y_id0.clone().cuda()
+    x_kp = torch.full((B, N), -1, dtype=torch.int64).cuda() if with_kp else None
+    y_kp = torch.full((B, N), -1, dtype=torch.int64).cuda() if with_kp else None
+    logits = torch.zeros(B, N, 2).cuda()
+    ops.query_decode_fwd(src=src.cuda(), w1_packed=ops.pack_weight(w1.cuda()), b1=b1.cuda(), slope=0.01, w2=w2.cuda().contiguous(), b2=b2.cuda(),
+                         plane=plane, Ltot=Ltot, x_bits=x_bits, y_bits=y_bits, x_id=x_id, y_id=y_id, perm=perm.cuda(), graph_sel=sel.cuda(),
+                         x_id_kp=x_kp, y_id_kp=y_kp, logits=logits)
+    err = float((logits.cpu().double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-3, err
+    lg = logits.cpu()
+    kp = perm[sel.long()].long()                                           # (B,N): plan position -> keypoint id
+    want_x = torch.full((B, N), float("nan")).scatter_(1, kp, lg[..., 0])
+    want_y = torch.full((B, N), float("nan")).scatter_(1, kp, lg[..., 1])
+    assert torch.equal(x_bits[:, plane].cpu(), want_x) and torch.equal(y_bits[:, plane].cpu(), want_y)
+    others = [l for l in range(Ltot) if l != plane]
+    assert torch.isnan(x_bits[:, others]).all() and torch.isnan(y_bits[:, others]).all()
+    nx, ny = x_id0 * 2 + (lg[..., 0] > 0).long(), y_id0 * 2 + (lg[..., 1] > 0).long()
+    assert torch.equal(x_id.cpu(), nx) and torch.equal(y_id.cpu(), ny)
+    if with_kp:
+        assert torch.equal(x_kp.cpu(), torch.zeros(B, N, dtype=torch.int64).scatter_(1, kp, nx))
+        assert torch.equal(y_kp.cpu(), torch.zeros(B, N, dtype=torch.int64).scatter_(1, kp, ny))
+
+
 # ------------------------------------------------------------------------------------------------ split-bf16 x3 GEMM
 @pytest.mark.parametrize("M,K1,K2,Nout,act", [(300, 64, 0, 128, False), (1000, 256, 64, 256, True), (257, 256, 256, 512, True),
                                                (128, 64, 0, 7, False), (513, 1024, 0, 600, False), (4096, 256, 0, 2, False)])

@@ -44,9 +44,9 @@ GRAPH_K = 20
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
 # `ncu --set full` capture of this command (profiles/)
 DOMINANT_KERNEL_DRAM_BYTES = 1.077e9 + 1.022e9
-DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r01_f_edgeconv.txt (ncu --set full, launch 0: dram read 1.077 GB + write 1.022 GB)"
-K3_KERNEL_DRAM_BYTES = 0.564e9 + 1.021e9
-K3_KERNEL_DRAM_SOURCE = "profiles/r01_f_taps_chain.txt (ncu --set full, launch 0: dram read 0.564 GB + write 1.021 GB)"
+DOMINANT_KERNEL_DRAM_SOURCE = "profiles/r02_h_edgeconv.txt (ncu --set full of bench.py --profile, launch 0: dram read 1.077 GB + write 1.022 GB)"
+K3_KERNEL_DRAM_BYTES = 0.567e9 + 1.022e9
+K3_KERNEL_DRAM_SOURCE = "profiles/r02_h_taps_chain_query_tail.txt (ncu --set full, launch 0: dram read 0.567 GB + write 1.022 GB)"
 LM_OBJECT_IDS = (1, 2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15)     # the 13 LM objects of test_lm.py:109
 
 

@@ -1,11 +1,3 @@
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu --timeout 200 -p no:cacheprovider -k "upsample or image" ) 2>&1 | grep -E "^E  |passed|failed|^FAILED|Error" | head
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/bench.log").read().strip().splitlines()[-1])
-print("ms/step", round(d["ms_per_step"], 3), "RoIs/s", round(d["value"]), "e2e", round(d["e2e"]["value"]),
-      "K2 ms", round(d["roofline"]["avg_launch_ms"], 4), "frac", round(d["roofline"]["frac"], 3),
-      "K3 ms", round(d["roofline_k3"]["avg_launch_ms"], 4), "gnn_only", round(d["gnn_only"]["ms_per_step"],3), "parity", d["parity"]["keypoint_agreement"], d["clocks"])
-PY
-tail -n 3 gpurun_out/bench.err
+( timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu --timeout 200 -p no:cacheprovider -k "upsample" ) 2>&1 | grep -E "^E  |passed|failed|^FAILED|Error" | head
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:upsample -c 6 --csv --log-file /tmp/l.csv python bench.py --profile --steps 1 --warmup 1 > /dev/null 2>&1; grep upsample /tmp/l.csv | awk -F'","' '{print $NF}' | tr -d '"' | tail -4

@@ -161,7 +161,7 @@ def build_case(wl, dev, seed_rank, N=None, K=None, batch=None):
         pool = LM_OBJECT_IDS if wl["ds"] == "lm" else wl["objs"]
         go = torch.Generator().manual_seed(777 + seed_rank)
         obj_ids = torch.tensor(pool)[torch.randint(0, len(pool), (B,), generator=go)].to(dev)
-    return dict(net=net, sd=sd, p3d=p3d, obj_ids=obj_ids, N=N, K=K, B=B)
+    return dict(net=net, sd=sd, p3d=p3d, obj_ids=obj_ids, N=N, K=K, B=B, init_only=wl["init_only"])
 
 
 def make_inputs(case, dev, dtype, seed_rank):
@@ -170,8 +170,9 @@ def make_inputs(case, dev, dtype, seed_rank):
     from checkerpose_b200 import synthetic as syn
     B = case["B"]
     gg = torch.Generator(device=dev).manual_seed(4321 + seed_rank)
+    first = 3 if case.get("init_only") else 1      # the init net alone reads only the 1024 x 8 x 8 map (init.py:111-112)
     feats = [torch.relu(torch.randn(B, c, s, s, generator=gg, device=dev)).to(dtype)
-             for c, s in zip(syn.HRNET_W18_DIMS[1:], syn.HRNET_W18_SIZES[1:])]
+             for c, s in zip(syn.HRNET_W18_DIMS[first:], syn.HRNET_W18_SIZES[first:])]
     bbox = syn.synthetic_bboxes(B, torch.Generator().manual_seed(99 + seed_rank)).to(dev)
     return feats, bbox
 
@@ -508,8 +509,9 @@ def run_ours(args):
             "config": {"workload": wl["text"], "name": wl["name"], "rois_per_gpu": B, "rois_total": B * world, "npoint": N, "graph_k": case["K"],
                        "objects": f"{wl['ds']}/{wl['objs'][0]}" if len(wl["objs"]) == 1 else f"{wl['ds']}: {len(wl['objs'])} graphs, selected per RoI",
                        "image_branch": "included (cuDNN, library part of the path)",
-                       "inputs": "the three HRNet maps the head reads (256@32^2, 512@16^2, 1024@8^2); the 128@64^2 map is never read "
-                                 "(pipeline.py:361,372) and is neither created nor uploaded",
+                       "inputs": ("the 1024@8^2 HRNet map (all the init net reads, init.py:111-112)" if wl["init_only"] else
+                                  "the three HRNet maps the head reads (256@32^2, 512@16^2, 1024@8^2); the 128@64^2 map is never read "
+                                  "(pipeline.py:361,372) and is neither created nor uploaded"),
                        "l2": "inputs (0.23 GB/step) and intermediates (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "collective": ("all_gather_into_tensor of the packed correspondence records (16 + 2N bytes per RoI) per step, on a side "
                                       "stream overlapped with the next step, complete inside the timed region") if world > 1 else "none (1 GPU)"},

@@ -93,8 +93,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 constexpr int RPT = TILE_M / (NUM_LOAD_WARPS * 2);   // rows per thread: 8 (a warp instruction covers 2 rows x 16 float4)
 
 struct RowInfo {       // per thread: its 8 rows of the current tile
-  int64_t lin[RPT];    // linear mode: row index, or -1 beyond M.  conv mode: pixel index b * H * W of the RoI, or -1
-  int oyx[RPT];        // conv mode: oy | ox << 16
+  int64_t base[RPT];   // LINEAR: row index.  CONV: element offset of input pixel (b, oy - pad, ox - pad), channel 0 (may lie outside
+                       // the map, even negative: only dereferenced for taps that land inside).  CONVT: pixel index b * H * W.
+                       // LINEAR / CONVT: -1 = row beyond M (CONV marks those rows in oyx)
+  int oyx[RPT];        // CONV / CONVT: oy | ox << 16
 };
 
 __device__ __forceinline__ void rows_of_tile(const X3Params& kp, int m_tile, int lw, int lane, RowInfo& ri) {
@@ -102,48 +104,67 @@ __device__ __forceinline__ void rows_of_tile(const X3Params& kp, int m_tile, int
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
     const int64_t m = (int64_t)m_tile * TILE_M + lw * 16 + i * 2 + (lane >> 4);
+    ri.oyx[i] = 0;
     if (m >= p.M) {
-      ri.lin[i] = -1;
-      ri.oyx[i] = 0;
+      ri.base[i] = -1;
+      ri.oyx[i] = 0x7fff7fff;      // CONV: every tap of such a row fails the bounds check (its base may be negative for real rows too)
     } else if (p.mode == CP_X3_LINEAR) {
-      ri.lin[i] = m;
-      ri.oyx[i] = 0;
+      ri.base[i] = m;
     } else {
       const int hw = p.Ho * p.Wo;
       const int64_t b = m / hw;
       const int rem = (int)(m - b * hw);
       const int oy = rem / p.Wo, ox = rem - oy * p.Wo;
-      ri.lin[i] = b * p.H * p.W;
       ri.oyx[i] = oy | (ox << 16);
+      ri.base[i] = p.mode == CP_X3_CONV ? ((b * p.H + (oy - p.pad)) * p.W + (ox - p.pad)) * p.k1 : b * p.H * p.W;
     }
   }
 }
 
-// global address of this thread's float4 of row i in K chunk kc; nullptr = zero fill
-__device__ __forceinline__ const float4* a_src(const X3Params& kp, const RowInfo& ri, int i, int kc, int c4) {
+// Position of a K chunk inside the reduction: LINEAR = which operand and column; CONV / CONVT = kernel tap and 64-channel
+// slice.  Advanced incrementally (no division per chunk: the loader warps are issue-bound on exactly this arithmetic --
+// ncu r02: 1150 warp instructions per loader warp and chunk with the division per row, 22 % of all samples).
+struct ChunkPos {
+  int ky, kx, cc;
+  __device__ __forceinline__ void reset() { ky = kx = cc = 0; }
+  __device__ __forceinline__ void next(int c_chunks, int KW) {
+    if (++cc == c_chunks) {
+      cc = 0;
+      if (++kx == KW) { kx = 0; ++ky; }
+    }
+  }
+};
+
+// this thread's float4 of its 8 rows for the chunk at `cp` (LINEAR: chunk index kc); zero fill outside the matrix / the map
+__device__ __forceinline__ void load_chunk(const X3Params& kp, const RowInfo& ri, const ChunkPos& cp, int kc, int c4, float4 (&v)[RPT]) {
   const cp_gemm_x3_params& p = kp.p;
-  if (ri.lin[i] < 0) return nullptr;
   if (p.mode == CP_X3_LINEAR) {
     const int k = kc * 64 + c4 * 4;
-    const float* s = k < p.k1 ? p.a1 + ri.lin[i] * p.ld1 + k : p.a2 + ri.lin[i] * p.ld2 + (k - p.k1);
-    return reinterpret_cast<const float4*>(s);
-  }
-  const int tap = kc / kp.c_chunks, cc = kc - tap * kp.c_chunks;
-  const int ky = tap / p.KW, kx = tap - ky * p.KW;
-  const int oy = ri.oyx[i] & 0xffff, ox = ri.oyx[i] >> 16;
-  int iy, ix;
-  if (p.mode == CP_X3_CONV) {
-    iy = oy - p.pad + ky;
-    ix = ox - p.pad + kx;
+    const bool first = k < p.k1;
+    const float* src = first ? p.a1 + k : p.a2 + (k - p.k1);
+    const int64_t ld = first ? p.ld1 : p.ld2;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+      v[i] = ri.base[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(src + ri.base[i] * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (p.mode == CP_X3_CONV) {
+    const int dy = cp.ky - p.pad, dx = cp.kx - p.pad;
+    const float* src = p.a1 + ((int64_t)cp.ky * p.W + cp.kx) * p.k1 + cp.cc * 64 + c4 * 4;   // + base[i] = pixel (oy + dy, ox + dx)
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int iy = (ri.oyx[i] & 0xffff) + dy, ix = (ri.oyx[i] >> 16) + dx;
+      const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+      v[i] = ok ? __ldg(reinterpret_cast<const float4*>(src + ri.base[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   } else {   // transposed convolution, stride 2: out[oy] += in[iy] * w[ky] with oy = 2 iy - pad + ky
-    const int ty = oy + p.pad - ky, tx = ox + p.pad - kx;
-    if ((ty | tx) & 1) return nullptr;
-    iy = ty >> 1;
-    ix = tx >> 1;
-    if (ty < 0 || tx < 0) return nullptr;
+    const float* src = p.a1 + cp.cc * 64 + c4 * 4;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int ty = (ri.oyx[i] & 0xffff) + p.pad - cp.ky, tx = (ri.oyx[i] >> 16) + p.pad - cp.kx;
+      const int iy = ty >> 1, ix = tx >> 1;
+      const bool ok = ri.base[i] >= 0 && ((ty | tx) & 1) == 0 && ty >= 0 && tx >= 0 && iy < p.H && ix < p.W;
+      v[i] = ok ? __ldg(reinterpret_cast<const float4*>(src + (ri.base[i] + (int64_t)iy * p.W + ix) * p.k1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
-  if (iy < 0 || ix < 0 || iy >= p.H || ix >= p.W) return nullptr;
-  return reinterpret_cast<const float4*>(p.a1 + (ri.lin[i] + (int64_t)iy * p.W + ix) * p.k1 + cc * 64 + c4 * 4);
 }
 
 __device__ void a_loader(const X3Params& kp, uint8_t* sm, Bars* bars, int lw, int lane) {
@@ -151,20 +172,18 @@ __device__ void a_loader(const X3Params& kp, uint8_t* sm, Bars* bars, int lw, in
   const uint32_t sm_base = smem_u32(sm);
   RowInfo ri;
   float4 cur[RPT], nxt[RPT];
+  ChunkPos pos;                              // position of the chunk being PREFETCHED
   uint32_t it = 0;                           // chunk counter over all tiles of this CTA
-  auto issue = [&](float4 (&v)[RPT], int kc) {
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      const float4* s = a_src(kp, ri, i, kc, c4);
-      v[i] = s ? __ldg(s) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x) {
     const int m_tile = tile / kp.nblk;
     rows_of_tile(kp, m_tile, lw, lane, ri);
-    issue(cur, 0);
+    pos.reset();
+    load_chunk(kp, ri, pos, 0, c4, cur);
     for (int kc = 0; kc < kp.KC; ++kc, ++it) {
-      if (kc + 1 < kp.KC) issue(nxt, kc + 1);          // next chunk's loads in flight while this one is converted
+      if (kc + 1 < kp.KC) {                  // next chunk's loads in flight while this one is converted
+        pos.next(kp.c_chunks, kp.p.KW);
+        load_chunk(kp, ri, pos, kc + 1, c4, nxt);
+      }
       const uint32_t s = it % STAGES;
       if (it >= STAGES) mbar_wait(&bars->empty[s], ((it / STAGES) - 1) & 1);
       const uint32_t a_hi = sm_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
@@ -180,8 +199,10 @@ __device__ void a_loader(const X3Params& kp, uint8_t* sm, Bars* bars, int lw, in
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->full[s]);
+      if (kc + 1 < kp.KC) {
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) cur[i] = nxt[i];
+        for (int i = 0; i < RPT; ++i) cur[i] = nxt[i];
+      }
     }
   }
 }
@@ -265,7 +286,9 @@ __device__ void epilogue(const X3Params& kp, const CUtensorMap* out_map, uint8_t
     const int col0 = nb * BN;
     const int cols = min(BN, kp.npad - col0);
     const uint32_t slot = tcount & 1;
-    mbar_wait_idle(&bars->acc_full[slot], (tcount >> 1) & 1);
+    // the epilogue warps share their schedulers with the loader warps and idle for a whole K loop (36-72 chunks of a
+    // convolution): back off instead of spinning on the barrier (their spin was 22 % of all issue samples, ncu r02)
+    while (!mbar_try_wait(&bars->acc_full[slot], (tcount >> 1) & 1)) __nanosleep(128);
     tc_fence_after_sync();
     const int64_t row0 = (int64_t)m_tile * TILE_M + q * 32;
     const int64_t row = row0 + lane;

@@ -379,6 +379,7 @@ def run_ours(args):
     torch.set_grad_enabled(False)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     head.set_compute_dtype(dtype)
+    head.set_image_branch(args.image_branch)
     wl = workload(args, world)
 
     def barrier():
@@ -427,7 +428,7 @@ def run_ours(args):
                 step(feats)
             ms_g = timed_loop(step, feats, args.steps, barrier, world, dev) / args.steps
         gnn_only = {"value": B * world / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
-                    "note": "up_net / patch_generator / seg_block outputs (cuDNN, library part of the path) reused from a previous step of the same "
+                    "note": "up_net / patch_generator / seg_block outputs (the image branch) reused from a previous step of the same "
                             "batch; everything else (conv1x1 GEMM, K2, K3, query MLPs, decode, records) runs"}
 
     # ---------------- e2e: pinned host buffers -> public API -> host, every step ----------------
@@ -508,7 +509,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": wl["text"], "name": wl["name"], "rois_per_gpu": B, "rois_total": B * world, "npoint": N, "graph_k": case["K"],
                        "objects": f"{wl['ds']}/{wl['objs'][0]}" if len(wl["objs"]) == 1 else f"{wl['ds']}: {len(wl['objs'])} graphs, selected per RoI",
-                       "image_branch": "included (cuDNN, library part of the path)",
+                       "image_branch": ("included: our implicit-GEMM convolutions on tcgen05 (cp_conv_bf16 / cp_gemm_x3), no library kernel"
+                                        if (args.image_branch == "tcgen05" or args.dtype == "fp32") else "included (cuDNN, library part of the path)"),
                        "inputs": ("the 1024@8^2 HRNet map (all the init net reads, init.py:111-112)" if wl["init_only"] else
                                   "the three HRNet maps the head reads (256@32^2, 512@16^2, 1024@8^2); the 128@64^2 map is never read "
                                   "(pipeline.py:361,372) and is neither created nor uploaded"),
@@ -576,6 +578,7 @@ def main():
     ap.add_argument("--sweep-n", default="512,1024,2048,4096")
     ap.add_argument("--sweep-k", default="8,16,20,32,40")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--image-branch", default="cudnn", choices=["tcgen05", "cudnn"], help="bf16 mode: whose convolutions run the image branch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: timed loop only, warm-up exactly --warmup")

@@ -2,7 +2,8 @@
 
 Public surface = the reference's own module API, re-exported from ``checkerpose_b200.model``,
 ``checkerpose_b200.common_ops`` and ``checkerpose_b200.binary_code_helper``; plus
-``set_compute_dtype`` ("fp32" validation mode / "bf16" tensor-core mode).
+``set_compute_dtype`` ("fp32": split-precision tensor-core mode that reproduces the reference's decode / "bf16": fastest mode)
+and ``set_image_branch`` (bf16 mode: "tcgen05" = our implicit-GEMM convolutions, "cudnn" = library convolutions).
 Importing the kernels requires the in-tree CUDA library (``python -m checkerpose_b200.build``).
 """
 __version__ = "0.1.0"
@@ -16,3 +17,13 @@ def set_compute_dtype(dtype):
 def get_compute_dtype():
     from . import head
     return head.get_compute_dtype()
+
+
+def set_image_branch(kind):
+    from . import head
+    head.set_image_branch(kind)
+
+
+def get_image_branch():
+    from . import head
+    return head.get_image_branch()

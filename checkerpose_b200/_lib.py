@@ -61,6 +61,19 @@ class GemmX3Params(C.Structure):
     ]
 
 
+class ConvBf16Params(C.Structure):
+    _fields_ = [
+        ("mode", c_i32),
+        ("a1", c_vp), ("ld1", c_i32), ("k1", c_i32),
+        ("a2", c_vp), ("ld2", c_i32), ("k2", c_i32),
+        ("H", c_i32), ("W", c_i32), ("Ho", c_i32), ("Wo", c_i32), ("KH", c_i32), ("KW", c_i32), ("pad", c_i32),
+        ("M", c_i64), ("K", c_i32),
+        ("w_packed", c_vp),
+        ("bias", c_vp), ("act", c_i32), ("slope", c_f32),
+        ("out", c_vp), ("ld_out", c_i32), ("Nout", c_i32),
+    ]
+
+
 class QueryDecodeParams(C.Structure):
     _fields_ = [
         ("B", c_i32), ("N", c_i32),
@@ -84,6 +97,7 @@ SIGNATURES = {
     "cp_edge_aggregate_staged_f32": (c_i32, [c_vp, C.POINTER(GraphPlanStruct), c_vp, c_f32, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cp_pnp_ransac": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, C.c_uint64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cp_query_decode_fwd": (c_i32, [C.POINTER(QueryDecodeParams), c_vp]),
+    "cp_conv_bf16": (c_i32, [C.POINTER(ConvBf16Params), c_vp]),
     "cp_graph_sel": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "cp_knn": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp_transpose_cn_to_nc": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

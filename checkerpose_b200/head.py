@@ -268,7 +268,7 @@ def init_head_node_major(init_net, feat_last, obj_ids, dtype):
     N = init_net.npoint
     dev = feat_last.device
     bias0 = None
-    if dtype == torch.bfloat16:
+    if dtype == torch.bfloat16 and _IMAGE_BRANCH == "cudnn":
         conv = _bf16_module(init_net.conv1x1)
         x0, bias0 = conv(feat_last.to(torch.bfloat16), defer_last_bias=True)   # bias applied by the layout change below
     else:
@@ -441,12 +441,16 @@ class _FoldedSeq:
 
 
 class _X3Seq:
-    """float32 mode of an image-branch conv stack (up_net block, patch_generator, seg_block, conv1x1): BatchNorm folded
-    into the weights, every convolution an implicit GEMM of the split-precision tensor-core kernel (cp_gemm_x3) over
-    NHWC fp32 maps with bias + ReLU in its epilogue; the bilinear x2 upsampling of the concatenated skip connection runs
-    on cp_upsample2x_cat_nhwc.  NCHW in, NCHW (channels_last strides) out."""
+    """An image-branch conv stack (up_net block, patch_generator, seg_block, conv1x1) on our own implicit-GEMM kernels:
+    BatchNorm folded into the weights, every convolution one launch over NHWC maps with bias + ReLU in its epilogue --
+    ``split=True`` (float32 mode): the split-precision tensor-core kernel cp_gemm_x3 on fp32 maps; ``split=False`` (bf16
+    mode, image branch "tcgen05"): cp_conv_bf16 on bf16 maps.  The bilinear x2 upsampling of the concatenated skip
+    connection runs on cp_upsample2x_cat_nhwc.  NCHW in, NCHW (channels_last strides) out."""
 
-    def __init__(self, module):
+    def __init__(self, module, split=True):
+        self.split = split
+        self.dtype = torch.float32 if split else torch.bfloat16
+        pack = ops.pack_weight_split if split else ops.pack_weight
         mods = list(module) if isinstance(module, nn.Sequential) else [module]
         self.ops = []
         i = 0
@@ -477,7 +481,7 @@ class _X3Seq:
                 if cin_pad != cin:
                     wk = F.pad(wk, (0, cin_pad - cin))
                 wm = wk.reshape(cout, kh * kw * cin_pad).contiguous()
-                self.ops.append(("convT" if tr else "conv", ops.pack_weight_split(wm), None if b is None else b.contiguous(),
+                self.ops.append(("convT" if tr else "conv", pack(wm), None if b is None else b.contiguous(),
                                  (cout, kh, kw, int(m.padding[0]), cin_pad), relu))
             elif isinstance(m, nn.UpsamplingBilinear2d):
                 if float(m.scale_factor) != 2.0:
@@ -489,16 +493,16 @@ class _X3Seq:
                 raise RuntimeError(f"unsupported layer in image branch: {type(m).__name__}")
             i += 1
 
-    @staticmethod
-    def _nhwc(x):
-        """NCHW fp32 (any strides) -> contiguous (B,H,W,C)."""
+    def _nhwc(self, x):
+        """NCHW (any strides) -> contiguous (B,H,W,C) of this stack's dtype."""
         v = x.permute(0, 2, 3, 1)
-        if v.is_contiguous():
+        if v.is_contiguous() and v.dtype == self.dtype:
             return v
         B, Cc, H, W = x.shape
-        return ops.to_node_major(x.contiguous().view(B, Cc, H * W), torch.float32).view(B, H, W, Cc)
+        return ops.to_node_major(x.contiguous().view(B, Cc, H * W), self.dtype).view(B, H, W, Cc)
 
     def __call__(self, x, skip=None):
+        conv = ops.gemm_x3_conv if self.split else ops.conv_bf16
         start = 0
         if self.ops[0][0] == "up":
             a = self._nhwc(x).permute(0, 3, 1, 2)
@@ -519,7 +523,7 @@ class _X3Seq:
                     Ho, Wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
                 else:
                     Ho, Wo = (H - 1) * 2 - 2 * pad + kh + 1, (W - 1) * 2 - 2 * pad + kw + 1
-                y = ops.gemm_x3_conv(y, ws, cout, kh, kw, pad, Ho, Wo, b, relu, 0.0, transposed=(kind == "convT"))
+                y = conv(y, ws, cout, kh, kw, pad, Ho, Wo, b, relu, 0.0, transposed=(kind == "convT"))
             elif kind == "relu":
                 y = torch.relu_(y)
             else:
@@ -529,7 +533,31 @@ class _X3Seq:
 
 def _x3_module(module):
     _require_eval(module)
-    return _PREP.get(module, ("x3seq",), lambda: _X3Seq(module))
+    return _PREP.get(module, ("x3seq",), lambda: _X3Seq(module, split=True))
+
+
+def _tc_module(module):
+    _require_eval(module)
+    return _PREP.get(module, ("tcseq",), lambda: _X3Seq(module, split=False))
+
+
+_IMAGE_BRANCH = "cudnn"
+
+
+def set_image_branch(kind: str) -> None:
+    """bf16 mode only: "tcgen05" = the image branch on cp_conv_bf16 (our implicit-GEMM kernel: 1.3-1.45 PFLOP/s on the 3x3
+    convolutions, no library kernel anywhere in the head), "cudnn" = the library convolutions (SURVEY 8a marks them as the
+    library part of the path).  Measured end to end: 15.2 vs 14.05 ms per step -- cuDNN's sm_100 kernels
+    are ahead on the two 64 x 64 convolutions, the transposed convolution and the narrow outputs -- so "cudnn" is the default
+    and "tcgen05" the switch for a head without library kernels.  The float32 mode never uses a library kernel."""
+    global _IMAGE_BRANCH
+    if kind not in ("tcgen05", "cudnn"):
+        raise ValueError("image branch must be 'tcgen05' or 'cudnn'")
+    _IMAGE_BRANCH = kind
+
+
+def get_image_branch() -> str:
+    return _IMAGE_BRANCH
 
 
 def _bf16_module(module):
@@ -559,8 +587,10 @@ def image_block(module, x, dtype, skip=None):
     to ``x`` along the channels first (pipeline.py:372)."""
     if _IMG_REUSE is not None and id(module) in _IMG_REUSE:
         return _IMG_REUSE[id(module)]
-    if dtype == torch.bfloat16:
+    if dtype == torch.bfloat16 and _IMAGE_BRANCH == "cudnn":
         y = _bf16_module(module)(x.to(torch.bfloat16), None if skip is None else skip.to(torch.bfloat16))
+    elif dtype == torch.bfloat16:
+        y = _tc_module(module)(x, skip)
     else:
         y = _x3_module(module)(x.float(), None if skip is None else skip.float())
     if _IMG_REUSE is not None:

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ChainLayer, ChainParams, EdgeConvParams, GemmX3Params, GraphPlanStruct, QueryDecodeParams, check, lib
+from ._lib import ChainLayer, ChainParams, ConvBf16Params, EdgeConvParams, GemmX3Params, GraphPlanStruct, QueryDecodeParams, check, lib
 
 CP_F32, CP_BF16 = 0, 1
 PRO_LOAD, PRO_AGG, PRO_TAPS = 0, 1, 2
@@ -264,6 +264,60 @@ def gemm_x3_conv(x_nhwc, w_split, nout, KH, KW, pad, Ho, Wo, bias=None, act=Fals
     p.bias, p.act, p.slope = _p(bias), int(bool(act)), float(slope)
     p.out, p.ld_out, p.Nout = _p(out), int(nout), int(nout)
     _gemm_x3(p, ("X3C", KH * KW * Cin, (int(nout),), OUT_F32, B * Ho * Wo, 0))
+    return out
+
+
+# ------------------------------------------------------------------- bf16 implicit-GEMM convolution on tcgen05
+def _conv_bf16(p: ConvBf16Params, sig):
+    if chain_event_log is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.cp_conv_bf16(C.byref(p), _stream()), "cp_conv_bf16")
+        e1.record()
+        chain_event_log.append((sig, e0, e1))
+    else:
+        check(lib.cp_conv_bf16(C.byref(p), _stream()), "cp_conv_bf16")
+    _count()
+
+
+def conv_bf16(x_nhwc, w_packed, nout, KH, KW, pad, Ho, Wo, bias=None, act=False, slope=0.0, transposed=False):
+    """Conv2d KH x KW stride 1 / ConvTranspose2d stride 2 over a bf16 NHWC map (B,H,W,Cin) -> (B,Ho,Wo,nout) bf16 as an implicit
+    GEMM on the tensor cores (cp_conv_bf16); W rows in (ky, kx, c) order, packed by pack_weight."""
+    _need_cuda(x_nhwc, bias, w_packed)
+    assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous() and x_nhwc.dim() == 4
+    B, H, W, Cin = x_nhwc.shape
+    out = torch.empty((B, Ho, Wo, nout), dtype=torch.bfloat16, device=x_nhwc.device)
+    p = ConvBf16Params()
+    p.mode = X3_CONVT if transposed else X3_CONV
+    p.a1, p.ld1, p.k1 = _p(x_nhwc), Cin, Cin
+    p.a2, p.ld2, p.k2 = None, 0, 0
+    p.H, p.W, p.Ho, p.Wo, p.KH, p.KW, p.pad = H, W, int(Ho), int(Wo), int(KH), int(KW), int(pad)
+    p.M, p.K = B * Ho * Wo, KH * KW * Cin
+    p.w_packed = _p(w_packed)
+    p.bias, p.act, p.slope = _p(bias), int(bool(act)), float(slope)
+    p.out, p.ld_out, p.Nout = _p(out), int(nout), int(nout)
+    _conv_bf16(p, ("CV", KH * KW * Cin, (int(nout),), OUT_BF16, B * Ho * Wo, 0))
+    return out
+
+
+def linear_bf16(a1, w_packed, nout, bias=None, act=False, slope=0.0, a2=None, out=None):
+    """y = act([a1|a2] @ W.T + bias), bf16 rows in / bf16 out, on cp_conv_bf16's LINEAR mode."""
+    _need_cuda(a1, a2, bias, w_packed)
+    assert a1.dtype == torch.bfloat16 and a1.is_contiguous()
+    K1 = a1.shape[-1]
+    M = a1.numel() // K1
+    K2 = 0 if a2 is None else a2.shape[-1]
+    if out is None:
+        out = torch.empty(a1.shape[:-1] + (nout,), dtype=torch.bfloat16, device=a1.device)
+    p = ConvBf16Params()
+    p.mode = X3_LINEAR
+    p.a1, p.ld1, p.k1 = _p(a1), K1, K1
+    p.a2, p.ld2, p.k2 = _p(a2), K2, K2
+    p.M, p.K = M, K1 + K2
+    p.w_packed = _p(w_packed)
+    p.bias, p.act, p.slope = _p(bias), int(bool(act)), float(slope)
+    p.out, p.ld_out, p.Nout = _p(out), out.stride(-2) if out.dim() > 1 else nout, int(nout)
+    _conv_bf16(p, ("LB", K1 + K2, (int(nout),), OUT_BF16, M, 0))
     return out
 
 

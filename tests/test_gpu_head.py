@@ -575,3 +575,35 @@ def test_cuda_graph_capture_replays_the_head(dtype):
             assert (a - b).abs().max() <= 0.15 * b.abs().max()
     if dtype == torch.float32:
         assert torch.equal(rec_g, rec_e)
+
+
+@pytest.mark.parametrize("name", ["head_lmo_ape_n512_b1", "head_lm15_n128_b3"])
+def test_bf16_image_branch_on_tcgen05_matches_the_library_branch(golden, name):
+    """bf16 mode with the image branch on our implicit-GEMM convolutions (cp_conv_bf16: up_net, patch_generator, seg_block,
+    conv1x1 -- no library kernel left in the head) against the same head on cuDNN and against the reference's golden outputs:
+    init logits within the bf16 budget of the reference, seg within 1e-2 of scale, decoded cells as close to the reference
+    as the library branch's."""
+    from checkerpose_b200 import head
+    g = golden(name)
+    ds, objs, N, B, seed, lm = HEAD_CASES[name]
+    p3d, sd, feats, obj_ids = head_case_inputs(name)
+    net = build_net(N, p3d, lm, sd)
+    head.set_compute_dtype(torch.bfloat16)
+    outs = {}
+    try:
+        for kind in ("cudnn", "tcgen05"):
+            head.set_image_branch(kind)
+            outs[kind] = run_net(net, feats, p3d, obj_ids, lm)
+    finally:
+        head.set_compute_dtype(torch.float32)
+        head.set_image_branch("cudnn")
+    for kind, (roi, xb, yb, seg, xid, yid) in outs.items():
+        for a, ref in ((roi, g["roi_bit"]), (xb[:, :3], g["x_bits"][:, :3]), (yb[:, :3], g["y_bits"][:, :3])):
+            d = a.cpu().numpy() - ref
+            assert np.sqrt((d ** 2).mean()) / np.sqrt((ref ** 2).mean()) < BF16_RMS and np.abs(d).max() / np.abs(ref).max() < BF16_MAX, kind
+        assert float(np.abs(seg.cpu().numpy() - g["seg"]).max() / np.abs(g["seg"]).max()) < 1.5e-2, kind
+        frac = float(((xid.cpu().numpy() == g["x_id"]) & (yid.cpu().numpy() == g["y_id"])).mean())
+        print(f"[bf16 {name}, image branch {kind}] cell agreement with the fp32 reference: {frac:.4f}")
+        assert frac > 0.70
+    a, b = outs["cudnn"], outs["tcgen05"]
+    assert float((a[3] - b[3]).abs().max() / a[3].abs().max()) < 2e-2          # seg: two bf16 conv stacks with different summation orders

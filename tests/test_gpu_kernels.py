@@ -393,6 +393,33 @@ def test_gemm_x3_conv_matches_fp64(cp, B, H, Cin, Cout, k, pad, transposed):
     assert out.shape == (B, Ho, Ho, Cout) and err < 2e-5, err
 
 
+@pytest.mark.parametrize("B,H,Cin,Cout,k,pad,transposed", [(3, 16, 256, 256, 3, 1, False), (2, 32, 64, 64, 2, 1, False),
+                                                           (2, 8, 128, 64, 3, 1, True), (5, 9, 64, 2, 1, 0, False), (2, 20, 512, 256, 3, 1, False)])
+def test_conv_bf16_matches_fp64(cp, B, H, Cin, Cout, k, pad, transposed):
+    """bf16 implicit-GEMM convolution on tcgen05 (cp_conv_bf16) against torch's float64 convolution on the same bf16-rounded
+    operands: only the fp32 accumulation order and the bf16 rounding of the output differ (1e-2 of north_star)."""
+    import torch.nn.functional as F
+    ops = cp.ops
+    g = torch.Generator().manual_seed(B + H + Cin + k)
+    x = torch.randn(B, Cin, H, H, generator=g).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g)
+    if transposed:
+        w = (torch.randn(Cin, Cout, k, k, generator=g) / (Cin * k * k / 4) ** 0.5).to(torch.bfloat16)
+        ref = F.conv_transpose2d(x.double(), w.double(), bias.double(), stride=2, padding=pad, output_padding=1)
+        wm = w.float().permute(1, 2, 3, 0).reshape(Cout, k * k * Cin)
+    else:
+        w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+        ref = F.conv2d(x.double(), w.double(), bias.double(), stride=1, padding=pad)
+        wm = w.float().permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)
+    ref = torch.relu(ref)
+    Ho = ref.shape[2]
+    out = ops.conv_bf16(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.pack_weight(wm.contiguous().cuda()), Cout, k, k, pad, Ho, Ho,
+                        bias.cuda(), True, 0.0, transposed)
+    err = float((out.float().cpu().double().permute(0, 3, 1, 2) - ref).abs().max() / ref.abs().max())
+    print(f"bf16 conv {'T' if transposed else ''} B={B} H={H} {Cin}->{Cout} k={k}: max err / max = {err:.2e}")
+    assert out.shape == (B, Ho, Ho, Cout) and out.dtype == torch.bfloat16 and err < 6e-3, err
+
+
 # ------------------------------------------------------------------------------------------------ tcgen05 chain
 def _bf16_round(t):
     return t.to(torch.bfloat16).float()

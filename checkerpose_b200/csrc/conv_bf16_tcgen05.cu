@@ -16,6 +16,7 @@
 //   warps 4-7   epilogue: tcgen05.ld -> + bias (BatchNorm folded) -> ReLU / LeakyReLU -> bf16 -> 32 x 32 tiles (SWIZZLE_64B) -> TMA
 //               tensor stores; two accumulators of 256 TMEM columns.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -53,6 +54,30 @@ struct Bars {
 struct CvParams {
   cp_conv_bf16_params p;
   int KC, c_chunks, num_m_tiles, nblk, num_tiles, npad, tma_out;
+};
+
+// Tiles of this CTA.  MC (weight multicast over a cluster of 2 CTAs, nblk == 1): cluster c takes tile pairs (2p, 2p + 1), the
+// CTA of rank r tile 2p + r; with an odd tile count the last pair's second CTA repeats the last tile (same values stored twice).
+template <bool MC>
+struct TileIt {
+  int first, step, count, last;
+  __device__ __forceinline__ explicit TileIt(const CvParams& kp) {
+    last = kp.num_tiles - 1;
+    if (MC) {
+      const int cid = (int)blockIdx.x >> 1, ncl = (int)gridDim.x >> 1, npairs = (kp.num_tiles + 1) >> 1;
+      first = 2 * cid + (int)(blockIdx.x & 1);
+      step = 2 * ncl;
+      count = cid < npairs ? (npairs - cid + ncl - 1) / ncl : 0;
+    } else {
+      first = (int)blockIdx.x;
+      step = (int)gridDim.x;
+      count = first < kp.num_tiles ? (kp.num_tiles - first + step - 1) / step : 0;
+    }
+  }
+  __device__ __forceinline__ int tile(int i) const {
+    const int t = first + i * step;
+    return t < last ? t : last;
+  }
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -124,6 +149,7 @@ struct ChunkPos {
   }
 };
 
+template <bool MC>
 __device__ void a_loader(const CvParams& kp, uint8_t* sm, Bars* bars, int tl) {
   const cp_conv_bf16_params& p = kp.p;
   const int piece = tl & 7;
@@ -133,7 +159,9 @@ __device__ void a_loader(const CvParams& kp, uint8_t* sm, Bars* bars, int tl) {
   RowInfo ri;
   ChunkPos pos;
   uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x) {
+  const TileIt<MC> tiles(kp);
+  for (int ti = 0; ti < tiles.count; ++ti) {
+    const int tile = tiles.tile(ti);
     rows_of_tile(kp, tile / kp.nblk, tl, ri);
     pos.reset();
     for (int kc = 0; kc < kp.KC; ++kc, ++it) {
@@ -179,11 +207,14 @@ __device__ void a_loader(const CvParams& kp, uint8_t* sm, Bars* bars, int tl) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+template <bool MC>
 __device__ void weight_producer(const CvParams& kp, uint8_t* sm, Bars* bars) {
   const cp_conv_bf16_params& p = kp.p;
   const uint8_t* wb = reinterpret_cast<const uint8_t*>(p.w_packed);
   uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x) {
+  const TileIt<MC> tiles(kp);
+  for (int ti = 0; ti < tiles.count; ++ti) {
+    const int tile = tiles.tile(ti);
     const int nb = tile % kp.nblk;
     const int col0 = nb * BN;
     const int cols = min(BN, kp.npad - col0);
@@ -191,6 +222,20 @@ __device__ void weight_producer(const CvParams& kp, uint8_t* sm, Bars* bars) {
     for (int kc = 0; kc < kp.KC; ++kc, ++it) {
       const uint32_t s = it % STAGES;
       if (it >= STAGES) mbar_wait_idle(&bars->empty[s], ((it / STAGES) - 1) & 1);
+      if (MC) {
+        // both CTAs of the cluster consume the same weight tile (nblk == 1): each fetches HALF of its rows from L2 and
+        // multicasts them into both CTAs' stage s; every CTA's barrier expects the whole tile
+        if (elect_one()) {
+          uint8_t* w_s = sm + s * STAGE_BYTES + A_BYTES;
+          const uint32_t half = (uint32_t)(cols / 2) * 128u, rank = blockIdx.x & 1;
+          mbar_arrive_expect_tx(&bars->full[s], (uint32_t)cols * 128u);
+          const uint8_t* src = cols == 256 ? wb + (size_t)rank * 128 * p.K * 2 + (size_t)kc * 128 * 128     // packed 128-row block `rank`
+                                           : wb + (size_t)kc * cols * 128 + (size_t)rank * half;               // half of the single block
+          bulk_g2s_multicast(w_s + rank * half, src, half, &bars->full[s], (uint16_t)3);
+        }
+        __syncwarp();
+        continue;
+      }
       if (elect_one()) {
         uint8_t* w_s = sm + s * STAGE_BYTES + A_BYTES;
         mbar_arrive_expect_tx(&bars->full[s], (uint32_t)cols * 128u);
@@ -203,10 +248,13 @@ __device__ void weight_producer(const CvParams& kp, uint8_t* sm, Bars* bars) {
   }
 }
 
+template <bool MC>
 __device__ void mma_issuer(const CvParams& kp, uint8_t* sm, Bars* bars, uint32_t tmem_base) {
   const uint32_t sm_base = smem_u32(sm);
   uint32_t it = 0, tcount = 0;
-  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++tcount) {
+  const TileIt<MC> tiles(kp);
+  for (int ti = 0; ti < tiles.count; ++ti, ++tcount) {
+    const int tile = tiles.tile(ti);
     const int nb = tile % kp.nblk;
     const int cols = min(BN, kp.npad - nb * BN);
     const uint32_t idesc = make_idesc_bf16_m128((uint32_t)cols);
@@ -221,7 +269,8 @@ __device__ void mma_issuer(const CvParams& kp, uint8_t* sm, Bars* bars, uint32_t
       if (elect_one()) {
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) mma_bf16_ss_lo(d, a_lo + 2 * k, w_lo + 2 * k, idesc, (uint32_t)((kc | (int)k) != 0));
-        mma_commit(&bars->empty[s]);
+        if (MC) mma_commit_multicast(&bars->empty[s], (uint16_t)3);   // stage s is refilled (by either CTA) only when BOTH have consumed it
+        else mma_commit(&bars->empty[s]);
         if (kc == kp.KC - 1) mma_commit(&bars->acc_full[slot]);
       }
       __syncwarp();
@@ -229,6 +278,7 @@ __device__ void mma_issuer(const CvParams& kp, uint8_t* sm, Bars* bars, uint32_t
   }
 }
 
+template <bool MC>
 __device__ void epilogue(const CvParams& kp, const CUtensorMap* out_map, uint8_t* sm, Bars* bars, uint32_t tmem_base, int q, int lane) {
   const cp_conv_bf16_params& p = kp.p;
   const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
@@ -236,7 +286,9 @@ __device__ void epilogue(const CvParams& kp, const CUtensorMap* out_map, uint8_t
   const int sw = (lane >> 1) & 3;      // SWIZZLE_64B: 16-byte chunk index ^= bits 1-2 of the row
   bf16* out = reinterpret_cast<bf16*>(p.out);
   uint32_t tcount = 0, nstore = 0;
-  for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x, ++tcount) {
+  const TileIt<MC> tiles(kp);
+  for (int ti = 0; ti < tiles.count; ++ti, ++tcount) {
+    const int tile = tiles.tile(ti);
     const int m_tile = tile / kp.nblk, nb = tile - m_tile * kp.nblk;
     const int col0 = nb * BN;
     const int cols = min(BN, kp.npad - col0);
@@ -302,6 +354,7 @@ __device__ void epilogue(const CvParams& kp, const CUtensorMap* out_map, uint8_t
   if (kp.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+template <bool MC>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_bf16_kernel(const __grid_constant__ CvParams kp, const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -310,7 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_bf16_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bars->full[s], 1 + LOAD_THREADS);     // weight producer (with the byte count) + every loader thread (asynchronously)
-      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->empty[s], MC ? 2 : 1);          // multicast: the MMA streams of both CTAs
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->acc_full[a], 1);
@@ -320,17 +373,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_bf16_kernel(const __grid_con
   }
   if (warp == 2) tmem_alloc(&bars->tmem_slot, TMEM_COLS);
   tc_fence_before_sync();
-  __syncthreads();
+  if (MC) cluster_sync_all();     // the peer's barriers exist before its multicast copies / commits arrive
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_slot;
 
-  if (warp >= LOAD_WARP0) a_loader(kp, sm, bars, threadIdx.x - LOAD_WARP0 * 32);
-  else if (warp >= EPI_WARP0) epilogue(kp, &out_map, sm, bars, tmem_base, warp - EPI_WARP0, lane);
-  else if (warp == 0) weight_producer(kp, sm, bars);
-  else if (warp == 1) mma_issuer(kp, sm, bars, tmem_base);
+  if (warp >= LOAD_WARP0) a_loader<MC>(kp, sm, bars, threadIdx.x - LOAD_WARP0 * 32);
+  else if (warp >= EPI_WARP0) epilogue<MC>(kp, &out_map, sm, bars, tmem_base, warp - EPI_WARP0, lane);
+  else if (warp == 0) weight_producer<MC>(kp, sm, bars);
+  else if (warp == 1) mma_issuer<MC>(kp, sm, bars, tmem_base);
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (MC) cluster_sync_all();     // no CTA leaves while the peer may still write into / arrive on its shared memory
+  else __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -373,10 +428,37 @@ extern "C" int cp_conv_bf16(const cp_conv_bf16_params* pp, cp_stream_t s) {
     if (rc != CP_OK) return rc;
   }
   const int num_sms = cp::num_sms();
-  const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
-  cudaError_t e = cudaFuncSetAttribute(conv_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  CP_REQUIRE(e == cudaSuccess, CP_E_CUDA, "cp_conv_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-  conv_bf16_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)s>>>(kp, map);
+  // weight multicast over clusters of 2 CTAs when every tile uses the same weight tile sequence (one column block) and its
+  // halves are whole swizzle atoms; CP_CONV_MULTICAST=0 forces the single-CTA kernel (A/B measurements)
+  const char* mc_env = getenv("CP_CONV_MULTICAST");
+  const bool mc = !(mc_env && mc_env[0] == '0') && kp.nblk == 1 && kp.num_tiles >= 2 && (kp.npad == 256 || kp.npad <= 128);
+  cudaError_t e;
+  if (!mc) {
+    const int grid = kp.num_tiles < num_sms ? kp.num_tiles : num_sms;
+    e = cudaFuncSetAttribute(conv_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    CP_REQUIRE(e == cudaSuccess, CP_E_CUDA, "cp_conv_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    conv_bf16_kernel<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)s>>>(kp, map);
+  } else {
+    const int want = 2 * ((kp.num_tiles + 1) / 2);
+    const int grid = want < (num_sms & ~1) ? want : (num_sms & ~1);
+    e = cudaFuncSetAttribute(conv_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    CP_REQUIRE(e == cudaSuccess, CP_E_CUDA, "cp_conv_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = (cudaStream_t)s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, conv_bf16_kernel<true>, kp, map);
+    CP_REQUIRE(e == cudaSuccess, CP_E_CUDA, "cp_conv_bf16: cluster launch failed: %s", cudaGetErrorString(e));
+  }
   CP_CHECK_LAUNCH("cp_conv_bf16");
   return CP_OK;
 }

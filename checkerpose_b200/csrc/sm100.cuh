@@ -194,6 +194,19 @@ __device__ __forceinline__ void mma2_commit_both(uint32_t bar_s) {
                ::"r"(bar_s), "h"((uint16_t)3) : "memory");
 }
 
+// ---- weight-tile multicast over a cluster (independent cta_group::1 MMAs per CTA, shared B operand) ----
+// One L2 read lands in the same shared-memory offset of every CTA in ctaMask and completes bytes on each CTA's mbarrier at
+// the same offset.
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+// tcgen05.commit of a cta_group::1 MMA stream arriving on the barrier at this offset in every CTA of ctaMask
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // Arrive on an mbarrier when all tcgen05 ops issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -440,7 +440,7 @@ class _FoldedSeq:
         return (x, None) if defer_last_bias else x
 
 
-class _X3Seq:
+class _OwnConvSeq:
     """An image-branch conv stack (up_net block, patch_generator, seg_block, conv1x1) on our own implicit-GEMM kernels:
     BatchNorm folded into the weights, every convolution one launch over NHWC maps with bias + ReLU in its epilogue --
     ``split=True`` (float32 mode): the split-precision tensor-core kernel cp_gemm_x3 on fp32 maps; ``split=False`` (bf16
@@ -533,12 +533,12 @@ class _X3Seq:
 
 def _x3_module(module):
     _require_eval(module)
-    return _PREP.get(module, ("x3seq",), lambda: _X3Seq(module, split=True))
+    return _PREP.get(module, ("x3seq",), lambda: _OwnConvSeq(module, split=True))
 
 
 def _tc_module(module):
     _require_eval(module)
-    return _PREP.get(module, ("tcseq",), lambda: _X3Seq(module, split=False))
+    return _PREP.get(module, ("tcseq",), lambda: _OwnConvSeq(module, split=False))
 
 
 _IMAGE_BRANCH = "cudnn"

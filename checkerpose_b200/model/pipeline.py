@@ -292,6 +292,18 @@ class PoseNet_GNNskip(head.DeviceScopedModule):
         with torch.cuda.device(img_feats[-1].device):
             return head.pose_head_forward(self, img_feats, obj_ids=obj_ids, stage=stage, bbox=bbox, packed=packed)
 
+    def forward_with_pose(self, img, p3d_normed, bbox, p3d_xyz, cam_K, stage=None, obj_ids=None, flag=ops.FLAG_ALL,
+                          reproj_thresh=2.0, iterations=150, seed=0):
+        """Extension: head + PnP front-end in one call (from_id_to_pose of test_network_with_test_data.py:32-119 for the whole
+        batch on the device).  p3d_xyz (G,N,3) object keypoints in mm (G = 1 or one cloud per graph, selected like the kNN
+        graphs), cam_K (3,3) or (B,3,3).  -> (the reference's 6-tuple, packed records, R (B,3,3), t (B,3), inlier counts (B))."""
+        out, packed = self.forward_with_correspondences(img, p3d_normed, bbox, stage=stage, obj_ids=obj_ids, packed=True)
+        with torch.cuda.device(packed.device):
+            sel = None if obj_ids is None else ops.graph_sel(obj_ids.to(packed.device), p3d_xyz.reshape(-1, self.npoint, 3).shape[0])
+            R, t, ninl = ops.pnp_ransac(packed, p3d_xyz, cam_K, graph_sel=sel, flag=flag, reproj_thresh=reproj_thresh,
+                                        iterations=iterations, seed=seed)
+        return out, packed, R, t, ninl
+
     def forward(self, img, p3d_normed, stage=None):
         img_feats = self.init_net.img_backbone(img)
         out, _ = head.pose_head_forward(self, img_feats, obj_ids=None, stage=stage)

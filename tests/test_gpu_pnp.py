@@ -146,3 +146,31 @@ def test_from_id_to_pose_dropin_matches_the_reference_call():
         from_id_to_pose(X, roi_xy_ori, K_LM, roi_mask_bit, xid, yid, use_progressivex=True)
     R, t = from_id_to_pose(X, roi_xy_ori, K_LM, np.zeros((N, 1), dtype=np.float32), xid, yid)
     assert np.array_equal(R, np.eye(3)) and np.array_equal(t, np.zeros((3, 1)))
+
+
+def test_forward_with_pose_runs_the_whole_chain():
+    """PoseNet_GNNskip.forward_with_pose = head -> packed records -> cp_pnp_ransac on the device; with random-init weights the
+    correspondences carry no pose, so this checks the plumbing: the records it solves are the ones forward_with_correspondences
+    returns, and the poses equal a separate pnp_ransac call on them."""
+    from checkerpose_b200 import head, ops
+    from checkerpose_b200.model import init, pipeline
+    from checkerpose_b200.model.backbone import FeatureListBackbone
+    N, B = 256, 3
+    g = torch.Generator().manual_seed(3)
+    xyz = syn.load_fps_xyz("lmo", 5, N)
+    p3d = syn.p3d_normed_tensor(xyz).cuda()
+    sd = syn.synthetic_state_dict(syn.head_param_spec(N), g)
+    inet = init.InitNet_GNN(npoint=N, p3d_normed=p3d, res_log2=3, backbone_name="hrnet_w18", pretrain_backbone=False, img_backbone=FeatureListBackbone())
+    net = pipeline.PoseNet_GNNskip(inet, npoint=N, p3d_normed=p3d, res_log2=6, local_k=2, num_graph_module=3)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    feats = [f.cuda() for f in syn.synthetic_features(B, g)]
+    bbox = syn.synthetic_bboxes(B, g).cuda()
+    K = torch.tensor(K_LM, dtype=torch.float32).cuda()
+    X = torch.tensor(xyz, dtype=torch.float32).view(1, N, 3).cuda()
+    head.set_compute_dtype(torch.float32)
+    out, packed, R, t, ninl = net.forward_with_pose(feats, p3d.expand(B, -1, -1), bbox, X, K, seed=5)
+    out2, packed2 = net.forward_with_correspondences(feats, p3d.expand(B, -1, -1), bbox, packed=True)
+    assert torch.equal(packed, packed2) and R.shape == (B, 3, 3) and t.shape == (B, 3) and ninl.shape == (B,)
+    R2, t2, n2 = ops.pnp_ransac(packed2, X, K, seed=5)
+    assert torch.equal(R, R2) and torch.equal(t, t2) and torch.equal(ninl, n2)

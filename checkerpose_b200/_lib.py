@@ -74,6 +74,25 @@ class ConvBf16Params(C.Structure):
     ]
 
 
+SLAB_MAX_TAPS, SLAB_MAX_PHASES = 9, 4
+
+
+class SlabPhase(C.Structure):
+    _fields_ = [("ntaps", c_i32), ("wtap", c_i32 * SLAB_MAX_TAPS), ("shift", c_i32 * SLAB_MAX_TAPS), ("out_off", c_i32)]
+
+
+class ConvSlabParams(C.Structure):
+    _fields_ = [
+        ("x", c_vp), ("B", c_i32), ("Hp", c_i32), ("Wp", c_i32), ("C", c_i32), ("ldx", c_i32),
+        ("w_packed", c_vp), ("K", c_i32),
+        ("bias", c_vp), ("act", c_i32), ("slope", c_f32),
+        ("out", c_vp), ("ld_out", c_i32), ("Nout", c_i32),
+        ("num_phases", c_i32), ("phase", SlabPhase * SLAB_MAX_PHASES),
+        ("vy0", c_i32), ("vy1", c_i32), ("vx0", c_i32), ("vx1", c_i32),
+        ("compact", c_i32), ("out_sb", c_i64), ("out_sy", c_i32), ("out_sx", c_i32),
+    ]
+
+
 class QueryDecodeParams(C.Structure):
     _fields_ = [
         ("B", c_i32), ("N", c_i32),
@@ -98,6 +117,10 @@ SIGNATURES = {
     "cp_pnp_ransac": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_i32, C.c_uint64, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "cp_query_decode_fwd": (c_i32, [C.POINTER(QueryDecodeParams), c_vp]),
     "cp_conv_bf16": (c_i32, [C.POINTER(ConvBf16Params), c_vp]),
+    "cp_conv_slab": (c_i32, [C.POINTER(ConvSlabParams), c_vp]),
+    "cp_zero_border_nhwc": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "cp_upsample2x_cat_nhwc_to": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_i64, c_i64,
+                                          c_i64, c_i32, c_i32, c_i32, c_vp]),
     "cp_graph_sel": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     "cp_knn": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "cp_transpose_cn_to_nc": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

@@ -54,12 +54,12 @@ int make_out_tensor_map(void* map128, void* out, int ncols, int ld_out, int N, i
   CP_REQUIRE(r == CUDA_SUCCESS, CP_E_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r);
   return CP_OK;
 }
-int make_bf16_operand_map(void* map128, const void* src, int64_t ncols, int64_t nrows, int64_t ld, const char* who) {
+int make_bf16_operand_map(void* map128, const void* src, int64_t ncols, int64_t nrows, int64_t ld, const char* who, int box_rows) {
   EncodeTiledFn enc = encode_tiled_fn();
   CP_REQUIRE(enc, CP_E_CUDA, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
   const cuuint64_t dims[2] = {(cuuint64_t)ncols, (cuuint64_t)nrows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, estr[2] = {1, 1};
   const CUresult r = enc(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(src), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -38,7 +38,7 @@ int make_out_tensor_map(void* map128, void* out, int ncols, int ld_out, int N, i
 
 // 2-D TMA tensor map (channels, rows) of a bf16 row-major matrix with a 64 x 128 box, SWIZZLE_128B: one box = one K chunk of a
 // 128-row A operand tile in the layout tcgen05.mma reads (TMA tensor LOADS; rows beyond the matrix are zero-filled).
-int make_bf16_operand_map(void* map128, const void* src, int64_t ncols, int64_t nrows, int64_t ld, const char* who);
+int make_bf16_operand_map(void* map128, const void* src, int64_t ncols, int64_t nrows, int64_t ld, const char* who, int box_rows = 128);
 
 // 2-D TMA tensor map (columns, rows) of an fp32 row-major matrix (rows, ld) with a 32 x 32 box in the SWIZZLE_128B layout
 // (one box row = 32 floats = 128 bytes): epilogues store 32 x 32 tiles through it; rows / columns beyond the matrix are clipped.

@@ -404,7 +404,7 @@ __device__ void weight_relay_peer(const EcParams& kp, Bars* bars) {
     for (int c = 0; c < kp.KC; ++c)
       for (int nb = 0; nb < kp.NB; ++nb) {
         mbar_wait(&bars->b_full[bs], b_par);
-        if (elect_one()) mbar_arrive_cluster(leader_b_full0 + bs * 8);
+        if (elect_one()) mbar_arrive_remote(leader_b_full0 + bs * 8);
         __syncwarp();
         if (++bs == B_STAGES) { bs = 0; b_par ^= 1; }
       }
@@ -625,7 +625,7 @@ __device__ void aggregator(const EcParams& kp, uint8_t* sm, Bars* bars, int aw, 
 #endif
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(a_full_leader0 + ab * 8);
+        if (PAIR) mbar_arrive_remote(a_full_leader0 + ab * 8);
         else mbar_arrive(&bars->a_full[ab]);
         mbar_arrive(&bars->stg_empty[it % NBAR]);
       }
@@ -694,7 +694,7 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(acc_empty_leader0 + (c0 >> ACC_SH) * 8);
+            if (PAIR) mbar_arrive_remote(acc_empty_leader0 + (c0 >> ACC_SH) * 8);
             else mbar_arrive(&bars->acc_empty[c0 >> ACC_SH]);
           }
         }
@@ -768,7 +768,7 @@ __device__ void epilogue_warps(const EcParams& kp, const CUtensorMap* out_map, u
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) mbar_arrive_cluster(acc_empty_leader0 + (c0 >> ACC_SH) * 8);
+          if (PAIR) mbar_arrive_remote(acc_empty_leader0 + (c0 >> ACC_SH) * 8);
           else mbar_arrive(&bars->acc_empty[c0 >> ACC_SH]);
         }
       }

@@ -83,7 +83,7 @@ template <> struct Wide<bf16> {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-upsample2x_cat_nhwc_kernel(Src a, Src b, T* __restrict__ out, int B, int H, int W, float scale_h, float scale_w) {
+upsample2x_cat_nhwc_kernel(Src a, Src b, T* __restrict__ out, int64_t o_sb, int o_sh, int o_sw, int B, int H, int W, float scale_h, float scale_w) {
   constexpr int V = Vec<T>::N;
   const int Ct = a.C + b.C;
   const int cv_per_px = Ct / V;
@@ -102,7 +102,7 @@ upsample2x_cat_nhwc_kernel(Src a, Src b, T* __restrict__ out, int B, int H, int 
   const int64_t s_sb = from_a ? a.sb : b.sb;
   const int s_sh = (int)(from_a ? a.sh : b.sh), s_sw = (int)(from_a ? a.sw : b.sw);      // < 2^31: checked by the host
   const T* sbase = reinterpret_cast<const T*>(from_a ? a.p : b.p) + (int64_t)bi * s_sb + c;
-  T* obase = out + (int64_t)bi * OH * OW * Ct + cv * V;
+  T* obase = out + (int64_t)bi * o_sb + cv * V;
 #pragma unroll 2
   for (int pass = 0; pass < 8; ++pass) {
     // pass -> 4 x 8 pixel block (pass >> 1 = block row, pass & 1 = block column) of the 16 x 16 patch
@@ -122,15 +122,15 @@ upsample2x_cat_nhwc_kernel(Src a, Src b, T* __restrict__ out, int B, int H, int 
     Wide<T>::fma(o, h0l * w1l, v01, false);
     Wide<T>::fma(o, h1l * w0l, v10, false);
     Wide<T>::fma(o, h1l * w1l, v11, false);
-    Vec<T>::store(obase + (oy * OW + ox) * Ct, o);
+    Vec<T>::store(obase + oy * o_sh + ox * o_sw, o);
   }
 }
 
 }  // namespace
 
-extern "C" int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_sw, int Ca, const void* b,
-                                      int64_t b_sb, int64_t b_sh, int64_t b_sw, int Cb, int dtype, void* out, int B,
-                                      int H, int W, cp_stream_t s) {
+extern "C" int cp_upsample2x_cat_nhwc_to(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_sw, int Ca, const void* b,
+                                         int64_t b_sb, int64_t b_sh, int64_t b_sw, int Cb, int dtype, void* out, int64_t o_sb,
+                                         int64_t o_sh, int64_t o_sw, int B, int H, int W, cp_stream_t s) {
   CP_REQUIRE(a && out && B > 0 && H > 0 && W > 0 && Ca > 0 && Cb >= 0, CP_E_INVALID, "cp_upsample2x_cat_nhwc: bad arguments");
   CP_REQUIRE(Cb == 0 || b, CP_E_INVALID, "cp_upsample2x_cat_nhwc: second source is NULL but Cb=%d", Cb);
   const int V = dtype == CP_F32 ? 4 : 8;
@@ -146,13 +146,48 @@ extern "C" int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh,
   const float sw = (2 * W > 1) ? (float)(W - 1) / (float)(2 * W - 1) : 0.f;
   const int cvp = (Ca + Cb) / V;
   CP_REQUIRE((int64_t)(H - 1) * a_sh + (int64_t)(W - 1) * a_sw < (1ll << 31) && (int64_t)(H - 1) * b_sh + (int64_t)(W - 1) * b_sw < (1ll << 31) &&
-             (int64_t)4 * H * W * (Ca + Cb) < (1ll << 31), CP_E_UNSUPPORTED, "cp_upsample2x_cat_nhwc: one RoI's map must stay below 2^31 elements");
+             (int64_t)(2 * H - 1) * o_sh + (int64_t)(2 * W - 1) * o_sw + Ca + Cb < (1ll << 31) && o_sb % V == 0 && o_sh % V == 0 && o_sw % V == 0 &&
+             o_sw >= Ca + Cb, CP_E_UNSUPPORTED, "cp_upsample2x_cat_nhwc: one RoI's map must stay below 2^31 elements");
   CP_REQUIRE(B <= 65535 && (2 * H + 15) / 16 <= 65535, CP_E_UNSUPPORTED, "cp_upsample2x_cat_nhwc: B=%d or H=%d too large for one grid", B, H);
   const dim3 g((unsigned)(((cvp + 7) / 8) * ((2 * W + 15) / 16)), (unsigned)((2 * H + 15) / 16), (unsigned)B);
   if (dtype == CP_F32)
-    upsample2x_cat_nhwc_kernel<float><<<g, 256, 0, (cudaStream_t)s>>>(sa, sb, (float*)out, B, H, W, sh, sw);
+    upsample2x_cat_nhwc_kernel<float><<<g, 256, 0, (cudaStream_t)s>>>(sa, sb, (float*)out, o_sb, (int)o_sh, (int)o_sw, B, H, W, sh, sw);
   else
-    upsample2x_cat_nhwc_kernel<bf16><<<g, 256, 0, (cudaStream_t)s>>>(sa, sb, (bf16*)out, B, H, W, sh, sw);
+    upsample2x_cat_nhwc_kernel<bf16><<<g, 256, 0, (cudaStream_t)s>>>(sa, sb, (bf16*)out, o_sb, (int)o_sh, (int)o_sw, B, H, W, sh, sw);
   CP_CHECK_LAUNCH("cp_upsample2x_cat_nhwc");
+  return CP_OK;
+}
+
+extern "C" int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_sw, int Ca, const void* b,
+                                      int64_t b_sb, int64_t b_sh, int64_t b_sw, int Cb, int dtype, void* out, int B,
+                                      int H, int W, cp_stream_t s) {
+  const int64_t Ct = (int64_t)Ca + Cb;
+  return cp_upsample2x_cat_nhwc_to(a, a_sb, a_sh, a_sw, Ca, b, b_sb, b_sh, b_sw, Cb, dtype, out, 4 * (int64_t)H * W * Ct, 2 * (int64_t)W * Ct, Ct,
+                                   B, H, W, s);
+}
+
+// ---- zero border of a stored NHWC map (the slab convolutions read their padding from the map itself) ----
+namespace {
+__global__ void zero_border_kernel(uint4* __restrict__ x, int Hp, int Wp, int row16) {
+  // one block row per (image, border pixel): 2*Wp + 2*(Hp-2) border pixels per image
+  const int nb = 2 * Wp + 2 * (Hp - 2);
+  const int e = (int)blockIdx.x % nb, b = (int)blockIdx.x / nb;
+  int py, px;
+  if (e < Wp) { py = 0; px = e; }
+  else if (e < 2 * Wp) { py = Hp - 1; px = e - Wp; }
+  else { const int r = e - 2 * Wp; py = 1 + (r >> 1); px = (r & 1) ? Wp - 1 : 0; }
+  uint4* row = x + (((int64_t)b * Hp + py) * Wp + px) * row16;
+  for (int i = threadIdx.x; i < row16; i += blockDim.x) row[i] = make_uint4(0, 0, 0, 0);
+}
+}  // namespace
+
+extern "C" int cp_zero_border_nhwc(void* x, int B, int Hp, int Wp, int C, int elem_bytes, cp_stream_t s) {
+  CP_REQUIRE(x && B > 0 && Hp >= 2 && Wp >= 2 && C > 0 && (elem_bytes == 2 || elem_bytes == 4), CP_E_INVALID, "cp_zero_border_nhwc: bad arguments");
+  CP_REQUIRE(((int64_t)C * elem_bytes) % 16 == 0 && ((uintptr_t)x & 15) == 0, CP_E_UNSUPPORTED, "cp_zero_border_nhwc: pixel rows must be whole 16-byte vectors");
+  const int64_t blocks = (int64_t)B * (2 * Wp + 2 * (Hp - 2));
+  CP_REQUIRE(blocks < (1ll << 31), CP_E_UNSUPPORTED, "cp_zero_border_nhwc: too many border pixels");
+  const int row16 = (int)((int64_t)C * elem_bytes / 16);
+  zero_border_kernel<<<(unsigned)blocks, row16 < 128 ? 32 : 64, 0, (cudaStream_t)s>>>((uint4*)x, Hp, Wp, row16);
+  CP_CHECK_LAUNCH("cp_zero_border_nhwc");
   return CP_OK;
 }

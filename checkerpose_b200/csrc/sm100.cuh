@@ -158,6 +158,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // release at cluster scope
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same arrive with the default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id): for
+// hand-offs whose payload was written by the async proxy (TMA bytes counted on a barrier, tcgen05 operations) and is read by
+// the async proxy again -- no generic-proxy data of this thread has to become visible to the other CTA.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar_s, uint32_t parity) {   // acquire at cluster scope
   uint32_t ok;
   asm volatile(
@@ -186,6 +192,31 @@ __device__ __forceinline__ void mma2_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, 
       "mov.b64 db, {%2, %5};\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
+// The same two MMAs with the A descriptor's HIGH word given as well: an operand that starts at a row r of a SWIZZLE_128B
+// tile which is not a multiple of 8 carries the row phase in the descriptor's base-offset field (bits 49-51:
+// (start address >> 7) & 7) -- the tap-shifted views of one activation slab in conv_slab_tcgen05.cu.
+constexpr uint32_t DESC_HI_SW128 = 0x40004040u;
+__device__ __forceinline__ uint32_t desc_hi_base_offset(uint32_t row_phase) { return DESC_HI_SW128 | ((row_phase & 7u) << 17); }
+__device__ __forceinline__ void mma_bf16_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128), "r"(a_hi)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_bf16_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128), "r"(a_hi)
       : "memory");
 }
 // arrive (when all tcgen05 ops issued so far by this thread have completed) on the barrier at this offset in BOTH CTAs

@@ -531,6 +531,89 @@ class _OwnConvSeq:
         return y.permute(0, 3, 1, 2)
 
 
+class _SlabConvSeq(_OwnConvSeq):
+    """The bf16 image branch on cp_conv_slab: every map of a block lives in a ZERO-BORDERED NHWC buffer (B, H+2, W+2, C), so
+    that a kernel tap is a row shift of one TMA-loaded activation slab (csrc/conv_slab_tcgen05.cu).  The x2 upsampling writes
+    the interior of such a buffer, 3x3 / 1x1 convolutions map buffer to buffer (their epilogue rewrites the border as zeros),
+    the transposed convolution of the first block runs as its four output parities, and patch_generator (2x2, padding 1)
+    leaves the layout with a contiguous (B, H+1, W+1, E) map.  The NCHW view handed back to the caller is the interior of the
+    buffer and remembers it (``_cp_padded``): the next block / patch_generator / seg_block pick the buffer up again
+    without a copy.  Shapes the slab kernel does not take (more than 256 output channels: conv1x1 of the init head) fall
+    back to the gather kernel cp_conv_bf16."""
+
+    def __init__(self, module):
+        super().__init__(module, split=False)
+
+    @staticmethod
+    def _view(buf):
+        y = buf[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
+        y._cp_padded = buf
+        return y
+
+    def _cl(self, x):
+        """(B,C,H,W) -> a bf16 view / copy with channel stride 1 (what the upsampling kernel reads)."""
+        if x.dtype == torch.bfloat16 and x.stride(1) == 1 and all(st % 8 == 0 for st in (x.stride(0), x.stride(2), x.stride(3))):
+            return x
+        return self._nhwc(x).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def _pad_channels(buf, cin_pad):
+        return buf if buf.shape[-1] == cin_pad else F.pad(buf, (0, cin_pad - buf.shape[-1]))
+
+    def __call__(self, x, skip=None):
+        kinds = self.ops
+        start = 0
+        buf = None          # zero-bordered (B,H+2,W+2,C) map, or None while y (plain NHWC) holds the current map
+        y = None
+        if kinds[0][0] == "up":
+            buf = ops.upsample2x_cat_padded(self._cl(x), None if skip is None else self._cl(skip))
+            start = 1
+        elif kinds[0][0] == "convT" and kinds[0][3][1:4] == (3, 3, 1) and kinds[0][3][0] <= 256:
+            _, ws, b, (cout, kh, kw, pad, cin_pad), relu = kinds[0]
+            if skip is not None:
+                x = torch.cat([x, skip], dim=1)
+            buf = ops.convT_slab(self._pad_channels(self._nhwc(x), cin_pad), ws, cout, b, relu, 0.0)
+            start = 1
+        else:
+            buf = getattr(x, "_cp_padded", None) if skip is None else None
+            if buf is None:
+                if skip is not None:
+                    x = torch.cat([x, skip], dim=1)
+                y = self._nhwc(x)
+        for kind, ws, b, geom, relu in kinds[start:]:
+            if kind == "relu":
+                cur = buf if buf is not None else y
+                torch.relu_(cur)
+                continue
+            if kind == "up":
+                src = self._view(buf) if buf is not None else y.permute(0, 3, 1, 2)
+                buf, y = ops.upsample2x_cat_padded(src, None), None
+                continue
+            cout, kh, kw, pad, cin_pad = geom
+            same = kind == "conv" and kh == kw and kh in (1, 3) and pad == kh // 2
+            full = kind == "conv" and kh == kw == 2 and pad == 1
+            if cout <= 256 and (same or full):
+                if buf is None:
+                    buf, y = F.pad(y, (0, 0, 1, 1, 1, 1)), None
+                buf = self._pad_channels(buf, cin_pad)
+                if same:
+                    buf = ops.conv_slab_same(buf, ws, cout, kh, kw, b, relu, 0.0)
+                else:
+                    y, buf = ops.conv_slab_full(buf, ws, cout, kh, kw, b, relu, 0.0), None
+                continue
+            # gather kernel on a contiguous map
+            if buf is not None:
+                y, buf = buf[:, 1:-1, 1:-1, :].contiguous(), None
+            y = self._pad_channels(y, cin_pad)
+            H, W = y.shape[1], y.shape[2]
+            if kind == "conv":
+                Ho, Wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+            else:
+                Ho, Wo = (H - 1) * 2 - 2 * pad + kh + 1, (W - 1) * 2 - 2 * pad + kw + 1
+            y = ops.conv_bf16(y, ws, cout, kh, kw, pad, Ho, Wo, b, relu, 0.0, transposed=(kind == "convT"))
+        return self._view(buf) if buf is not None else y.permute(0, 3, 1, 2)
+
+
 def _x3_module(module):
     _require_eval(module)
     return _PREP.get(module, ("x3seq",), lambda: _OwnConvSeq(module, split=True))
@@ -538,7 +621,7 @@ def _x3_module(module):
 
 def _tc_module(module):
     _require_eval(module)
-    return _PREP.get(module, ("tcseq",), lambda: _OwnConvSeq(module, split=False))
+    return _PREP.get(module, ("tcseq",), lambda: _SlabConvSeq(module))
 
 
 _IMAGE_BRANCH = "cudnn"

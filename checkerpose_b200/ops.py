@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ChainLayer, ChainParams, ConvBf16Params, EdgeConvParams, GemmX3Params, GraphPlanStruct, QueryDecodeParams, check, lib
+from ._lib import ChainLayer, ChainParams, ConvBf16Params, ConvSlabParams, EdgeConvParams, GemmX3Params, GraphPlanStruct, QueryDecodeParams, check, lib
 
 CP_F32, CP_BF16 = 0, 1
 PRO_LOAD, PRO_AGG, PRO_TAPS = 0, 1, 2
@@ -318,6 +318,144 @@ def linear_bf16(a1, w_packed, nout, bias=None, act=False, slope=0.0, a2=None, ou
     p.bias, p.act, p.slope = _p(bias), int(bool(act)), float(slope)
     p.out, p.ld_out, p.Nout = _p(out), out.stride(-2) if out.dim() > 1 else nout, int(nout)
     _conv_bf16(p, ("LB", K1 + K2, (int(nout),), OUT_BF16, M, 0))
+    return out
+
+
+# ------------------------------------------------------------------- slab convolutions over zero-bordered maps
+def _conv_slab(p: ConvSlabParams, sig):
+    if chain_event_log is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.cp_conv_slab(C.byref(p), _stream()), "cp_conv_slab")
+        e1.record()
+        chain_event_log.append((sig, e0, e1))
+    else:
+        check(lib.cp_conv_slab(C.byref(p), _stream()), "cp_conv_slab")
+    _count()
+
+
+def _slab_common(xp, w_packed, K, nout, bias, act, slope):
+    _need_cuda(xp, bias, w_packed)
+    assert xp.dtype == torch.bfloat16 and xp.is_contiguous() and xp.dim() == 4
+    B, Hp, Wp, Cin = xp.shape
+    p = ConvSlabParams()
+    p.x, p.B, p.Hp, p.Wp, p.C, p.ldx = _p(xp), B, Hp, Wp, Cin, Cin
+    p.w_packed, p.K = _p(w_packed), int(K)
+    p.bias, p.act, p.slope = _p(bias), int(bool(act)), float(slope)
+    p.Nout = int(nout)
+    return p
+
+
+def zero_border(xp):
+    """Zero the one-pixel border of a stored NHWC map (B,Hp,Wp,C) in place."""
+    _need_cuda(xp)
+    assert xp.is_contiguous() and xp.dim() == 4
+    B, Hp, Wp, Cc = xp.shape
+    check(lib.cp_zero_border_nhwc(_p(xp), B, Hp, Wp, Cc, xp.element_size(), _stream()), "cp_zero_border_nhwc")
+    _count()
+    return xp
+
+
+def conv_slab_same(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
+    """Conv2d KH x KW (odd sizes), stride 1, "same" padding, over a ZERO-BORDERED bf16 map xp (B, H+2, W+2, Cin) -> the
+    zero-bordered (B, H+2, W+2, nout) map of the result (border rows written as zeros): chains of such convolutions never
+    leave the padded layout.  W rows in (ky, kx, c) order, packed by pack_weight.  The border must cover the kernel's reach
+    (KH, KW <= 3)."""
+    B, Hp, Wp, Cin = xp.shape
+    assert KH % 2 == 1 and KW % 2 == 1 and KH <= 3 and KW <= 3
+    p = _slab_common(xp, w_packed, KH * KW * Cin, nout, bias, act, slope)
+    out = torch.empty((B, Hp, Wp, nout), dtype=torch.bfloat16, device=xp.device)
+    p.out, p.ld_out = _p(out), int(nout)
+    p.num_phases = 1
+    ph = p.phase[0]
+    ph.ntaps = KH * KW
+    for ky in range(KH):
+        for kx in range(KW):
+            t = ky * KW + kx
+            ph.wtap[t] = t
+            ph.shift[t] = (ky - KH // 2) * Wp + (kx - KW // 2)
+    p.vy0, p.vy1, p.vx0, p.vx1 = 1, Hp - 1, 1, Wp - 1
+    p.compact = 0
+    _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
+    return out
+
+
+def conv_slab_full(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
+    """Conv2d KH x KW, stride 1, padding k-1 ("full": patch_generator's Conv2d(kernel 2, padding 1), pipeline.py:144-145) over a
+    zero-bordered bf16 map xp (B, H+2, W+2, Cin) whose border covers that padding (KH, KW <= 2) -> contiguous
+    (B, H+KH-1, W+KW-1, nout)."""
+    B, Hp, Wp, Cin = xp.shape
+    assert 1 <= KH <= 2 and 1 <= KW <= 2
+    H, W = Hp - 2, Wp - 2
+    Ho, Wo = H + KH - 1, W + KW - 1
+    p = _slab_common(xp, w_packed, KH * KW * Cin, nout, bias, act, slope)
+    out = torch.empty((B, Ho, Wo, nout), dtype=torch.bfloat16, device=xp.device)
+    p.out, p.ld_out = _p(out), int(nout)
+    p.num_phases = 1
+    ph = p.phase[0]
+    ph.ntaps = KH * KW
+    # output (oy, ox) sits at grid position (py, px) = (oy + 2 - KH, ox + 2 - KW) and reads stored pixels (py + ky, px + kx)
+    for ky in range(KH):
+        for kx in range(KW):
+            t = ky * KW + kx
+            ph.wtap[t] = t
+            ph.shift[t] = ky * Wp + kx
+    ph.out_off = 0
+    p.vy0, p.vy1, p.vx0, p.vx1 = 2 - KH, 2 - KH + Ho, 2 - KW, 2 - KW + Wo
+    p.compact, p.out_sb, p.out_sy, p.out_sx = 1, Ho * Wo, Wo, 1
+    _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
+    return out
+
+
+def convT_slab(x_nhwc, w_packed, nout, bias=None, act=False, slope=0.0):
+    """ConvTranspose2d(kernel 3, stride 2, padding 1, output_padding 1) (pipeline.py:187-197) of a bf16 NHWC map (B,H,W,Cin)
+    as the FOUR output parities of the result, each a small convolution over the input with its own 1 / 2 / 2 / 4 taps (9 tap
+    GEMMs in all; the gather formulation of cp_conv_bf16 multiplies 36, three quarters of them zeros).  Returns the
+    zero-bordered (B, 2H+2, 2W+2, nout) map.  W rows in (ky, kx, c) order, packed by pack_weight."""
+    B, H, W, Cin = x_nhwc.shape
+    xp = torch.zeros((B, H + 1, W + 1, Cin), dtype=torch.bfloat16, device=x_nhwc.device)    # zero row / column after the map
+    xp[:, :H, :W] = x_nhwc
+    Hp, Wp = H + 1, W + 1
+    p = _slab_common(xp, w_packed, 9 * Cin, nout, bias, act, slope)
+    OHp, OWp = 2 * H + 2, 2 * W + 2
+    out = torch.zeros((B, OHp, OWp, nout), dtype=torch.bfloat16, device=xp.device)
+    p.out, p.ld_out = _p(out), int(nout)
+    p.num_phases = 4
+    # oy = 2 iy - 1 + ky: even rows oy = 2i take ky = 1 from iy = i; odd rows oy = 2i + 1 take ky = 2 from iy = i and ky = 0 from i + 1
+    taps1 = {0: [(1, 0)], 1: [(2, 0), (0, 1)]}          # parity -> [(k, input offset)]
+    for dy in range(2):
+        for dx in range(2):
+            ph = p.phase[dy * 2 + dx]
+            t = 0
+            for ky, sy in taps1[dy]:
+                for kx, sx in taps1[dx]:
+                    ph.wtap[t] = ky * 3 + kx
+                    ph.shift[t] = sy * Wp + sx
+                    t += 1
+            ph.ntaps = t
+            ph.out_off = (dy + 1) * OWp + dx + 1          # (2i + dy, 2j + dx) inside the zero border
+    p.vy0, p.vy1, p.vx0, p.vx1 = 0, H, 0, W
+    p.compact, p.out_sb, p.out_sy, p.out_sx = 1, OHp * OWp, 2 * OWp, 2
+    _conv_slab(p, ("CS", 9 * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
+    return out
+
+
+def upsample2x_cat_padded(a, b=None):
+    """upsample2x_cat writing the interior of a zero-bordered NHWC map: returns (B, 2H+2, 2W+2, Ca+Cb) contiguous."""
+    _need_cuda(a, b)
+    B, Ca, H, W = a.shape
+    Cb = 0 if b is None else b.shape[1]
+    if b is not None and (b.shape[0] != B or b.shape[2:] != a.shape[2:] or b.dtype != a.dtype):
+        raise RuntimeError("upsample2x_cat: sources disagree in shape or dtype")
+    Ct = Ca + Cb
+    out = torch.empty((B, 2 * H + 2, 2 * W + 2, Ct), dtype=a.dtype, device=a.device)
+    zero_border(out)
+    sa = _nhwc_strides(a)
+    sb = (0, 0, 0) if b is None else _nhwc_strides(b)
+    inner = out[:, 1:, 1:]
+    check(lib.cp_upsample2x_cat_nhwc_to(_p(a), sa[0], sa[1], sa[2], Ca, _p(b), sb[0], sb[1], sb[2], Cb, _dt(a), C.c_void_p(inner.data_ptr()),
+                                        out.stride(0), out.stride(1), out.stride(2), B, H, W, _stream()), "cp_upsample2x_cat_nhwc_to")
+    _count()
     return out
 
 

@@ -136,6 +136,42 @@ typedef struct {
 } cp_conv_bf16_params;
 int cp_conv_bf16(const cp_conv_bf16_params* p, cp_stream_t s);
 
+/* ---- slab convolution (conv_slab_tcgen05.cu): the same convolutions over ZERO-BORDERED maps, each activation read once ----
+ * x is a stored NHWC map (B, Hp, Wp, C) bf16 that includes its own zero border, seen as a matrix of G = B*Hp*Wp rows.  Over
+ * that flat row index a kernel tap is a CONSTANT row shift: the output at grid position g reads rows g + shift[t], so one
+ * tile of 128 consecutive positions needs one slab of 128 + max(shift) - min(shift) rows per 64-channel slice -- loaded ONCE
+ * by TMA (SWIZZLE_128B, rows outside the matrix zero-filled) and presented to tcgen05.mma once per tap through a descriptor
+ * whose start address is moved by shift rows (cp_conv_bf16 gathers every tap's rows again: 9x the activation traffic of a
+ * 3x3 convolution).  CTA pairs (cta_group::2, M = 256) share each weight tile: every CTA loads half of it.
+ *   out[g, :Nout] = act(sum_t x[g + shift[t], :C] . W[:, wtap[t]*C : (wtap[t]+1)*C]^T + bias)   for positions g = (b, py, px)
+ *   with vy0 <= py < vy1, vx0 <= px < vx1 (the window that holds real outputs);
+ *   compact == 0: out has the grid of x ((G, ld_out) rows); rows outside the window are written as ZEROS, so the result is again
+ *                 a zero-bordered map (Conv2d 3x3 pad 1 chains: get_gdrn_upsample_module pipeline.py:195-208);
+ *   compact == 1: only window rows are written, to row b*out_sb + (py-vy0)*out_sy + (px-vx0)*out_sx + phase.out_off (pixels):
+ *                 patch_generator (Conv2d 2x2 pad 1, pipeline.py:144-145: 65 x 65 outputs of a 64 x 64 map) and the four
+ *                 output parities ("phases") of ConvTranspose2d stride 2 (pipeline.py:187-197), each with its own tap list.
+ * W: cp_pack_weight of the (Nout, K) matrix, K = (number of weight taps) * C in tap-major order; C % 64 == 0; Nout <= 256. */
+#define CP_SLAB_MAX_TAPS 9
+#define CP_SLAB_MAX_PHASES 4
+typedef struct {
+  int ntaps;
+  int wtap[CP_SLAB_MAX_TAPS];
+  int shift[CP_SLAB_MAX_TAPS];
+  int out_off;
+} cp_slab_phase;
+typedef struct {
+  const void* x; int B, Hp, Wp, C, ldx;
+  const void* w_packed; int K;
+  const float* bias; int act; float slope;
+  void* out; int ld_out; int Nout;
+  int num_phases; cp_slab_phase phase[CP_SLAB_MAX_PHASES];
+  int vy0, vy1, vx0, vx1;
+  int compact; int64_t out_sb; int out_sy, out_sx;
+} cp_conv_slab_params;
+int cp_conv_slab(const cp_conv_slab_params* p, cp_stream_t s);
+/* zero the one-pixel border of a stored NHWC map (B, Hp, Wp, C) of elem_bytes-wide elements (row pitch C) */
+int cp_zero_border_nhwc(void* x, int B, int Hp, int Wp, int C, int elem_bytes, cp_stream_t s);
+
 /* ---- K2: EdgeConv -----------------------------------------------------------------------------
  * Aggregation half:  y[b,i,c] = lrelu(max_k z[b, idx[g(b), i, k], c] + z[b, i, Co + c]),  z (B,N,2Co).
  * idx (G, N, K) int32; graph_sel (B) int32 selects the per-RoI graph (pipeline_lm.py:55-57), NULL =>
@@ -268,6 +304,10 @@ int cp_sample_taps(const void* patches, int dtype, int Hp, int Wp, int E, int ta
 int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_sw, int Ca, const void* b,
                            int64_t b_sb, int64_t b_sh, int64_t b_sw, int Cb, int dtype, void* out, int B,
                            int H, int W, cp_stream_t s);
+/* the same with the output's element strides (o_sb, o_sh, o_sw >= Ca+Cb) given: writes the interior of a zero-bordered map */
+int cp_upsample2x_cat_nhwc_to(const void* a, int64_t a_sb, int64_t a_sh, int64_t a_sw, int Ca, const void* b,
+                              int64_t b_sb, int64_t b_sh, int64_t b_sw, int Cb, int dtype, void* out, int64_t o_sb,
+                              int64_t o_sh, int64_t o_sw, int B, int H, int W, cp_stream_t s);
 
 /* ---- K4: sign-bit decode ------------------------------------------------------------------------
  * Init stage (pipeline.py:363-369): logits (B*N, ld) f32 rows = [roi, x_0..x_{L-1}, y_0..y_{L-1}].

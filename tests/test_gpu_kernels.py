@@ -420,6 +420,72 @@ def test_conv_bf16_matches_fp64(cp, B, H, Cin, Cout, k, pad, transposed):
     assert out.shape == (B, Ho, Ho, Cout) and out.dtype == torch.bfloat16 and err < 6e-3, err
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("kind,B,H,W,Cin,Cout", [("same3", 3, 16, 16, 256, 256), ("same3", 3, 10, 12, 64, 64), ("same3", 2, 64, 64, 128, 256),
+                                                 ("same1", 5, 9, 9, 64, 7), ("full2", 2, 32, 32, 64, 64), ("full2", 3, 11, 9, 128, 64),
+                                                 ("convT", 2, 8, 8, 128, 256), ("convT", 3, 5, 7, 64, 64)])
+def test_conv_slab_matches_fp64(cp, monkeypatch, pair, kind, B, H, W, Cin, Cout):
+    """Slab convolution (cp_conv_slab: one TMA-loaded activation slab per channel slice, every tap a row-shifted tcgen05
+    descriptor over it; CTA pairs and single CTAs) against torch's float64 convolution on the same bf16-rounded operands, and
+    the zero border of the maps it hands on.  Odd tile counts, ragged maps, narrow outputs, all four transposed parities."""
+    import torch.nn.functional as F
+    ops = cp.ops
+    monkeypatch.setenv("CP_SLAB_PAIR", pair)
+    g = torch.Generator().manual_seed(B + H + Cin + len(kind))
+    x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g)
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    xp = F.pad(xh, (0, 0, 1, 1, 1, 1)).contiguous()
+    bordered = True
+    if kind == "convT":
+        w = (torch.randn(Cin, Cout, 3, 3, generator=g) / (Cin * 9 / 4) ** 0.5).to(torch.bfloat16)
+        ref = F.conv_transpose2d(x.double(), w.double(), bias.double(), stride=2, padding=1, output_padding=1)
+        wm = w.float().permute(1, 2, 3, 0).reshape(Cout, 9 * Cin)
+        out = ops.convT_slab(xh, ops.pack_weight(wm.contiguous().cuda()), Cout, bias.cuda(), True, 0.0)
+    else:
+        k = int(kind[-1])
+        w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+        wm = w.float().permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)
+        wp = ops.pack_weight(wm.contiguous().cuda())
+        if kind.startswith("same"):
+            ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)
+            out = ops.conv_slab_same(xp, wp, Cout, k, k, bias.cuda(), True, 0.0)
+        else:
+            ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k - 1)
+            out = ops.conv_slab_full(xp, wp, Cout, k, k, bias.cuda(), True, 0.0)
+            bordered = False
+    ref = torch.relu(ref).permute(0, 2, 3, 1)
+    out = out.float().cpu().double()
+    if bordered:
+        assert out.shape == (B, ref.shape[1] + 2, ref.shape[2] + 2, Cout)
+        edge = out.clone()
+        edge[:, 1:-1, 1:-1] = 0
+        assert float(edge.abs().max()) == 0.0, "the border of a slab convolution's output must be zeros"
+        out = out[:, 1:-1, 1:-1]
+    assert out.shape == ref.shape
+    err = float((out - ref).abs().max() / ref.abs().max())
+    print(f"slab {kind} pair={pair} B={B} {H}x{W} {Cin}->{Cout}: max err / max = {err:.2e}")
+    assert err < 6e-3, err
+
+
+def test_zero_border_and_padded_upsample(cp):
+    """cp_zero_border_nhwc + cp_upsample2x_cat_nhwc_to: the padded upsampling equals the plain one inside a zero border."""
+    ops = cp.ops
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(3, 7, 9, 64, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2)
+    b = torch.randn(3, 7, 9, 32, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2)
+    plain = ops.upsample2x_cat(a, b).permute(0, 2, 3, 1)
+    buf = ops.upsample2x_cat_padded(a, b)
+    assert buf.shape == (3, 16, 20, 96)
+    assert torch.equal(buf[:, 1:-1, 1:-1], plain)
+    edge = buf.clone()
+    edge[:, 1:-1, 1:-1] = 0
+    assert float(edge.float().abs().max()) == 0.0
+    # the source may itself be the interior of a bordered map (strided view)
+    again = ops.upsample2x_cat_padded(buf[:, 1:-1, 1:-1].permute(0, 3, 1, 2), None)
+    assert torch.equal(again[:, 1:-1, 1:-1], ops.upsample2x_cat(plain.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last), None).permute(0, 2, 3, 1))
+
+
 # ------------------------------------------------------------------------------------------------ tcgen05 chain
 def _bf16_round(t):
     return t.to(torch.bfloat16).float()

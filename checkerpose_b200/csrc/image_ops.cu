@@ -166,16 +166,13 @@ extern "C" int cp_upsample2x_cat_nhwc(const void* a, int64_t a_sb, int64_t a_sh,
                                    B, H, W, s);
 }
 
-// ---- zero border of a stored NHWC map (the slab convolutions read their padding from the map itself) ----
+// ---- zero border of a bordered NHWC map (the slab convolutions read their padding from the map itself): the LAST row and
+//      the LAST column of every image ----
 namespace {
 __global__ void zero_border_kernel(uint4* __restrict__ x, int Hp, int Wp, int row16) {
-  // one block row per (image, border pixel): 2*Wp + 2*(Hp-2) border pixels per image
-  const int nb = 2 * Wp + 2 * (Hp - 2);
+  const int nb = Wp + Hp - 1;       // border pixels per image
   const int e = (int)blockIdx.x % nb, b = (int)blockIdx.x / nb;
-  int py, px;
-  if (e < Wp) { py = 0; px = e; }
-  else if (e < 2 * Wp) { py = Hp - 1; px = e - Wp; }
-  else { const int r = e - 2 * Wp; py = 1 + (r >> 1); px = (r & 1) ? Wp - 1 : 0; }
+  const int py = e < Wp ? Hp - 1 : e - Wp, px = e < Wp ? e : Wp - 1;
   uint4* row = x + (((int64_t)b * Hp + py) * Wp + px) * row16;
   for (int i = threadIdx.x; i < row16; i += blockDim.x) row[i] = make_uint4(0, 0, 0, 0);
 }
@@ -184,7 +181,7 @@ __global__ void zero_border_kernel(uint4* __restrict__ x, int Hp, int Wp, int ro
 extern "C" int cp_zero_border_nhwc(void* x, int B, int Hp, int Wp, int C, int elem_bytes, cp_stream_t s) {
   CP_REQUIRE(x && B > 0 && Hp >= 2 && Wp >= 2 && C > 0 && (elem_bytes == 2 || elem_bytes == 4), CP_E_INVALID, "cp_zero_border_nhwc: bad arguments");
   CP_REQUIRE(((int64_t)C * elem_bytes) % 16 == 0 && ((uintptr_t)x & 15) == 0, CP_E_UNSUPPORTED, "cp_zero_border_nhwc: pixel rows must be whole 16-byte vectors");
-  const int64_t blocks = (int64_t)B * (2 * Wp + 2 * (Hp - 2));
+  const int64_t blocks = (int64_t)B * (Wp + Hp - 1);
   CP_REQUIRE(blocks < (1ll << 31), CP_E_UNSUPPORTED, "cp_zero_border_nhwc: too many border pixels");
   const int row16 = (int)((int64_t)C * elem_bytes / 16);
   zero_border_kernel<<<(unsigned)blocks, row16 < 128 ? 32 : 64, 0, (cudaStream_t)s>>>((uint4*)x, Hp, Wp, row16);

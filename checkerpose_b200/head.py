@@ -532,11 +532,12 @@ class _OwnConvSeq:
 
 
 class _SlabConvSeq(_OwnConvSeq):
-    """The bf16 image branch on cp_conv_slab: every map of a block lives in a ZERO-BORDERED NHWC buffer (B, H+2, W+2, C), so
-    that a kernel tap is a row shift of one TMA-loaded activation slab (csrc/conv_slab_tcgen05.cu).  The x2 upsampling writes
+    """The bf16 image branch on cp_conv_slab: every map of a block lives in a BORDERED NHWC buffer (B, H+1, W+1, C) -- a zero
+    last row and last column per image, which over the flat pixel index are all four borders at once -- so that a kernel tap is
+    a row shift of one TMA-loaded activation slab (csrc/conv_slab_tcgen05.cu).  The x2 upsampling writes
     the interior of such a buffer, 3x3 / 1x1 convolutions map buffer to buffer (their epilogue rewrites the border as zeros),
     the transposed convolution of the first block runs as its four output parities, and patch_generator (2x2, padding 1)
-    leaves the layout with a contiguous (B, H+1, W+1, E) map.  The NCHW view handed back to the caller is the interior of the
+    produces exactly the stored grid as a contiguous (B, H+1, W+1, E) map.  The NCHW view handed back to the caller is the interior of the
     buffer and remembers it (``_cp_padded``): the next block / patch_generator / seg_block pick the buffer up again
     without a copy.  Shapes the slab kernel does not take (more than 256 output channels: conv1x1 of the init head) fall
     back to the gather kernel cp_conv_bf16."""
@@ -546,7 +547,7 @@ class _SlabConvSeq(_OwnConvSeq):
 
     @staticmethod
     def _view(buf):
-        y = buf[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
+        y = buf[:, :-1, :-1, :].permute(0, 3, 1, 2)
         y._cp_padded = buf
         return y
 
@@ -594,7 +595,7 @@ class _SlabConvSeq(_OwnConvSeq):
             full = kind == "conv" and kh == kw == 2 and pad == 1
             if cout <= 256 and (same or full):
                 if buf is None:
-                    buf, y = F.pad(y, (0, 0, 1, 1, 1, 1)), None
+                    buf, y = ops.to_bordered(y), None
                 buf = self._pad_channels(buf, cin_pad)
                 if same:
                     buf = ops.conv_slab_same(buf, ws, cout, kh, kw, b, relu, 0.0)
@@ -603,7 +604,7 @@ class _SlabConvSeq(_OwnConvSeq):
                 continue
             # gather kernel on a contiguous map
             if buf is not None:
-                y, buf = buf[:, 1:-1, 1:-1, :].contiguous(), None
+                y, buf = buf[:, :-1, :-1, :].contiguous(), None
             y = self._pad_channels(y, cin_pad)
             H, W = y.shape[1], y.shape[2]
             if kind == "conv":

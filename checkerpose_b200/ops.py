@@ -347,7 +347,7 @@ def _slab_common(xp, w_packed, K, nout, bias, act, slope):
 
 
 def zero_border(xp):
-    """Zero the one-pixel border of a stored NHWC map (B,Hp,Wp,C) in place."""
+    """Zero the shared border (last row and last column of every image) of a stored NHWC map (B,H+1,W+1,C) in place."""
     _need_cuda(xp)
     assert xp.is_contiguous() and xp.dim() == 4
     B, Hp, Wp, Cc = xp.shape
@@ -356,11 +356,19 @@ def zero_border(xp):
     return xp
 
 
+# Bordered layout of the slab convolutions: an image (H, W) is stored as (H+1, W+1) with a zero LAST row and LAST column.
+# Over the flat pixel index of the whole batch that one column is the right border of its row and the left border of the
+# next one, the one row is the bottom border of its image and the top border of the next one; the rows before the first
+# image and after the last one are zero-filled by the TMA unit.  (H+1)(W+1) / HW = 3 % more rows at 64 x 64.
+def to_bordered(x_nhwc):
+    """(B,H,W,C) -> the bordered (B,H+1,W+1,C) copy."""
+    return torch.nn.functional.pad(x_nhwc, (0, 0, 0, 1, 0, 1))
+
+
 def conv_slab_same(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
-    """Conv2d KH x KW (odd sizes), stride 1, "same" padding, over a ZERO-BORDERED bf16 map xp (B, H+2, W+2, Cin) -> the
-    zero-bordered (B, H+2, W+2, nout) map of the result (border rows written as zeros): chains of such convolutions never
-    leave the padded layout.  W rows in (ky, kx, c) order, packed by pack_weight.  The border must cover the kernel's reach
-    (KH, KW <= 3)."""
+    """Conv2d KH x KW (1 or 3), stride 1, "same" padding, over a bordered bf16 map xp (B, H+1, W+1, Cin) -> the bordered
+    (B, H+1, W+1, nout) map of the result (its border written as zeros): chains of such convolutions never leave the
+    layout.  W rows in (ky, kx, c) order, packed by pack_weight."""
     B, Hp, Wp, Cin = xp.shape
     assert KH % 2 == 1 and KW % 2 == 1 and KH <= 3 and KW <= 3
     p = _slab_common(xp, w_packed, KH * KW * Cin, nout, bias, act, slope)
@@ -374,35 +382,31 @@ def conv_slab_same(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
             t = ky * KW + kx
             ph.wtap[t] = t
             ph.shift[t] = (ky - KH // 2) * Wp + (kx - KW // 2)
-    p.vy0, p.vy1, p.vx0, p.vx1 = 1, Hp - 1, 1, Wp - 1
+    p.vy0, p.vy1, p.vx0, p.vx1 = 0, Hp - 1, 0, Wp - 1
     p.compact = 0
     _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
     return out
 
 
 def conv_slab_full(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
-    """Conv2d KH x KW, stride 1, padding k-1 ("full": patch_generator's Conv2d(kernel 2, padding 1), pipeline.py:144-145) over a
-    zero-bordered bf16 map xp (B, H+2, W+2, Cin) whose border covers that padding (KH, KW <= 2) -> contiguous
-    (B, H+KH-1, W+KW-1, nout)."""
+    """Conv2d 2 x 2, stride 1, padding 1 (patch_generator, pipeline.py:144-145) over a bordered bf16 map xp (B, H+1, W+1, Cin)
+    -> contiguous (B, H+1, W+1, nout): output (oy, ox) reads pixels (oy-1+ky, ox-1+kx), so the output grid IS the stored grid
+    -- every row of the launch is a real output."""
     B, Hp, Wp, Cin = xp.shape
-    assert 1 <= KH <= 2 and 1 <= KW <= 2
-    H, W = Hp - 2, Wp - 2
-    Ho, Wo = H + KH - 1, W + KW - 1
+    assert KH == 2 and KW == 2
     p = _slab_common(xp, w_packed, KH * KW * Cin, nout, bias, act, slope)
-    out = torch.empty((B, Ho, Wo, nout), dtype=torch.bfloat16, device=xp.device)
+    out = torch.empty((B, Hp, Wp, nout), dtype=torch.bfloat16, device=xp.device)
     p.out, p.ld_out = _p(out), int(nout)
     p.num_phases = 1
     ph = p.phase[0]
     ph.ntaps = KH * KW
-    # output (oy, ox) sits at grid position (py, px) = (oy + 2 - KH, ox + 2 - KW) and reads stored pixels (py + ky, px + kx)
     for ky in range(KH):
         for kx in range(KW):
             t = ky * KW + kx
             ph.wtap[t] = t
-            ph.shift[t] = ky * Wp + kx
-    ph.out_off = 0
-    p.vy0, p.vy1, p.vx0, p.vx1 = 2 - KH, 2 - KH + Ho, 2 - KW, 2 - KW + Wo
-    p.compact, p.out_sb, p.out_sy, p.out_sx = 1, Ho * Wo, Wo, 1
+            ph.shift[t] = (ky - 1) * Wp + (kx - 1)
+    p.vy0, p.vy1, p.vx0, p.vx1 = 0, Hp, 0, Wp
+    p.compact = 0
     _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
     return out
 
@@ -411,14 +415,14 @@ def convT_slab(x_nhwc, w_packed, nout, bias=None, act=False, slope=0.0):
     """ConvTranspose2d(kernel 3, stride 2, padding 1, output_padding 1) (pipeline.py:187-197) of a bf16 NHWC map (B,H,W,Cin)
     as the FOUR output parities of the result, each a small convolution over the input with its own 1 / 2 / 2 / 4 taps (9 tap
     GEMMs in all; the gather formulation of cp_conv_bf16 multiplies 36, three quarters of them zeros).  Returns the
-    zero-bordered (B, 2H+2, 2W+2, nout) map.  W rows in (ky, kx, c) order, packed by pack_weight."""
+    bordered (B, 2H+1, 2W+1, nout) map.  W rows in (ky, kx, c) order, packed by pack_weight."""
     B, H, W, Cin = x_nhwc.shape
-    xp = torch.zeros((B, H + 1, W + 1, Cin), dtype=torch.bfloat16, device=x_nhwc.device)    # zero row / column after the map
-    xp[:, :H, :W] = x_nhwc
+    xp = to_bordered(x_nhwc)
     Hp, Wp = H + 1, W + 1
     p = _slab_common(xp, w_packed, 9 * Cin, nout, bias, act, slope)
-    OHp, OWp = 2 * H + 2, 2 * W + 2
-    out = torch.zeros((B, OHp, OWp, nout), dtype=torch.bfloat16, device=xp.device)
+    OHp, OWp = 2 * H + 1, 2 * W + 1
+    out = torch.empty((B, OHp, OWp, nout), dtype=torch.bfloat16, device=xp.device)
+    zero_border(out)
     p.out, p.ld_out = _p(out), int(nout)
     p.num_phases = 4
     # oy = 2 iy - 1 + ky: even rows oy = 2i take ky = 1 from iy = i; odd rows oy = 2i + 1 take ky = 2 from iy = i and ky = 0 from i + 1
@@ -433,7 +437,7 @@ def convT_slab(x_nhwc, w_packed, nout, bias=None, act=False, slope=0.0):
                     ph.shift[t] = sy * Wp + sx
                     t += 1
             ph.ntaps = t
-            ph.out_off = (dy + 1) * OWp + dx + 1          # (2i + dy, 2j + dx) inside the zero border
+            ph.out_off = dy * OWp + dx
     p.vy0, p.vy1, p.vx0, p.vx1 = 0, H, 0, W
     p.compact, p.out_sb, p.out_sy, p.out_sx = 1, OHp * OWp, 2 * OWp, 2
     _conv_slab(p, ("CS", 9 * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
@@ -441,19 +445,18 @@ def convT_slab(x_nhwc, w_packed, nout, bias=None, act=False, slope=0.0):
 
 
 def upsample2x_cat_padded(a, b=None):
-    """upsample2x_cat writing the interior of a zero-bordered NHWC map: returns (B, 2H+2, 2W+2, Ca+Cb) contiguous."""
+    """upsample2x_cat writing the interior of a bordered NHWC map: returns (B, 2H+1, 2W+1, Ca+Cb) contiguous."""
     _need_cuda(a, b)
     B, Ca, H, W = a.shape
     Cb = 0 if b is None else b.shape[1]
     if b is not None and (b.shape[0] != B or b.shape[2:] != a.shape[2:] or b.dtype != a.dtype):
         raise RuntimeError("upsample2x_cat: sources disagree in shape or dtype")
     Ct = Ca + Cb
-    out = torch.empty((B, 2 * H + 2, 2 * W + 2, Ct), dtype=a.dtype, device=a.device)
+    out = torch.empty((B, 2 * H + 1, 2 * W + 1, Ct), dtype=a.dtype, device=a.device)
     zero_border(out)
     sa = _nhwc_strides(a)
     sb = (0, 0, 0) if b is None else _nhwc_strides(b)
-    inner = out[:, 1:, 1:]
-    check(lib.cp_upsample2x_cat_nhwc_to(_p(a), sa[0], sa[1], sa[2], Ca, _p(b), sb[0], sb[1], sb[2], Cb, _dt(a), C.c_void_p(inner.data_ptr()),
+    check(lib.cp_upsample2x_cat_nhwc_to(_p(a), sa[0], sa[1], sa[2], Ca, _p(b), sb[0], sb[1], sb[2], Cb, _dt(a), _p(out),
                                         out.stride(0), out.stride(1), out.stride(2), B, H, W, _stream()), "cp_upsample2x_cat_nhwc_to")
     _count()
     return out

@@ -137,7 +137,9 @@ typedef struct {
 int cp_conv_bf16(const cp_conv_bf16_params* p, cp_stream_t s);
 
 /* ---- slab convolution (conv_slab_tcgen05.cu): the same convolutions over ZERO-BORDERED maps, each activation read once ----
- * x is a stored NHWC map (B, Hp, Wp, C) bf16 that includes its own zero border, seen as a matrix of G = B*Hp*Wp rows.  Over
+ * x is a stored NHWC map (B, Hp, Wp, C) bf16 that includes its own zero border (one zero row after and one zero column right
+ * of every image are enough: over the flat index they are the top / left border of what follows; rows before the first and
+ * after the last image are zero-filled by the TMA unit), seen as a matrix of G = B*Hp*Wp rows.  Over
  * that flat row index a kernel tap is a CONSTANT row shift: the output at grid position g reads rows g + shift[t], so one
  * tile of 128 consecutive positions needs one slab of 128 + max(shift) - min(shift) rows per 64-channel slice -- loaded ONCE
  * by TMA (SWIZZLE_128B, rows outside the matrix zero-filled) and presented to tcgen05.mma once per tap through a descriptor
@@ -169,7 +171,8 @@ typedef struct {
   int compact; int64_t out_sb; int out_sy, out_sx;
 } cp_conv_slab_params;
 int cp_conv_slab(const cp_conv_slab_params* p, cp_stream_t s);
-/* zero the one-pixel border of a stored NHWC map (B, Hp, Wp, C) of elem_bytes-wide elements (row pitch C) */
+/* zero the border of a bordered NHWC map (B, Hp, Wp, C) of elem_bytes-wide elements (row pitch C): the LAST row and the LAST
+ * column of every image (over the flat pixel index they serve as the right / left and bottom / top borders at once) */
 int cp_zero_border_nhwc(void* x, int B, int Hp, int Wp, int C, int elem_bytes, cp_stream_t s);
 
 /* ---- K2: EdgeConv -----------------------------------------------------------------------------

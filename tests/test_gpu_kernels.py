@@ -435,7 +435,7 @@ def test_conv_slab_matches_fp64(cp, monkeypatch, pair, kind, B, H, W, Cin, Cout)
     x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16)
     bias = torch.randn(Cout, generator=g)
     xh = x.permute(0, 2, 3, 1).contiguous().cuda()
-    xp = F.pad(xh, (0, 0, 1, 1, 1, 1)).contiguous()
+    xp = ops.to_bordered(xh).contiguous()
     bordered = True
     if kind == "convT":
         w = (torch.randn(Cin, Cout, 3, 3, generator=g) / (Cin * 9 / 4) ** 0.5).to(torch.bfloat16)
@@ -457,11 +457,11 @@ def test_conv_slab_matches_fp64(cp, monkeypatch, pair, kind, B, H, W, Cin, Cout)
     ref = torch.relu(ref).permute(0, 2, 3, 1)
     out = out.float().cpu().double()
     if bordered:
-        assert out.shape == (B, ref.shape[1] + 2, ref.shape[2] + 2, Cout)
+        assert out.shape == (B, ref.shape[1] + 1, ref.shape[2] + 1, Cout)
         edge = out.clone()
-        edge[:, 1:-1, 1:-1] = 0
+        edge[:, :-1, :-1] = 0
         assert float(edge.abs().max()) == 0.0, "the border of a slab convolution's output must be zeros"
-        out = out[:, 1:-1, 1:-1]
+        out = out[:, :-1, :-1]
     assert out.shape == ref.shape
     err = float((out - ref).abs().max() / ref.abs().max())
     print(f"slab {kind} pair={pair} B={B} {H}x{W} {Cin}->{Cout}: max err / max = {err:.2e}")
@@ -476,14 +476,14 @@ def test_zero_border_and_padded_upsample(cp):
     b = torch.randn(3, 7, 9, 32, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2)
     plain = ops.upsample2x_cat(a, b).permute(0, 2, 3, 1)
     buf = ops.upsample2x_cat_padded(a, b)
-    assert buf.shape == (3, 16, 20, 96)
-    assert torch.equal(buf[:, 1:-1, 1:-1], plain)
+    assert buf.shape == (3, 15, 19, 96)
+    assert torch.equal(buf[:, :-1, :-1], plain)
     edge = buf.clone()
-    edge[:, 1:-1, 1:-1] = 0
+    edge[:, :-1, :-1] = 0
     assert float(edge.float().abs().max()) == 0.0
     # the source may itself be the interior of a bordered map (strided view)
-    again = ops.upsample2x_cat_padded(buf[:, 1:-1, 1:-1].permute(0, 3, 1, 2), None)
-    assert torch.equal(again[:, 1:-1, 1:-1], ops.upsample2x_cat(plain.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last), None).permute(0, 2, 3, 1))
+    again = ops.upsample2x_cat_padded(buf[:, :-1, :-1].permute(0, 3, 1, 2), None)
+    assert torch.equal(again[:, :-1, :-1], ops.upsample2x_cat(plain.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last), None).permute(0, 2, 3, 1))
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 chain

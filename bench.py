@@ -340,6 +340,21 @@ def kernel_rooflines(log, ms_total, steps, B, N, dtype, world):
     return roof, roof_k3
 
 
+def conv_roofline(log, ms_total, steps, world):
+    """Image branch "tcgen05": the slab convolutions (cp_conv_slab) of the timed loop against the sustained bf16 tensor peak.
+    Flops are those of the convolutions proper (the border rows the kernel also multiplies are not counted)."""
+    _, _, tf_sus, peak_src = load_peaks()
+    cs = [(a.elapsed_time(b), sig[5]) for sig, a, b in log if sig[0] == "CS"]
+    if not cs:
+        return None
+    ms = sum(t for t, _ in cs)
+    flops = 2.0 * sum(m for _, m in cs)
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "conv_slab_kernel (up_net 3x3 / transposed parities / patch_generator 2x2 / seg_block, bf16, all launches)",
+            "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "peak_source": peak_src + ", sustained bf16",
+            "launches_per_step": len(cs) / steps, "ms_per_step": ms / steps, "share_of_step": ms / ms_total if world == 1 else None}
+
+
 def timed_loop(step, feats, steps, barrier, world, dev):
     """Exactly ``steps`` steps bracketed by barrier + synchronize on both sides; CUDA events; max over ranks (ms)."""
     import torch.distributed as dist
@@ -414,6 +429,7 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = B * world / (ms_step * 1e-3)
     roof, roof_k3 = kernel_rooflines(log, ms_total, args.steps, B, N, dtype, world)
+    roof_conv = conv_roofline(log, ms_total, args.steps, world)
 
     if args.profile:   # under ncu: no e2e / CPU legs, numbers printed here are NOT bench values
         if rank == 0:
@@ -523,7 +539,7 @@ def run_ours(args):
                             "previous step's gather + D2H overlap compute on side streams; with N > 1 rank 0 reads back all gathered records "
                             "(d2h_bytes_per_step), the other ranks their own shard",
                     "numa_bound": numa_bound},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_k3": roof_k3, "gnn_only": gnn_only,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_k3": roof_k3, "roofline_conv": roof_conv, "gnn_only": gnn_only,
             "parity": parity, "cpu_baseline": cpu_base,
         }))
     if world > 1:

@@ -36,14 +36,15 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int NTHREADS = 256;
 constexpr int EPI_WARP0 = 4;
-constexpr int A_BUFS = 2;
+constexpr int MAX_AB = 6;
 constexpr int MAX_WS = 8;
 constexpr int EPI_TILE_BYTES = 32 * 64;   // 32 rows x 32 bf16 (SWIZZLE_64B) per TMA store
 constexpr int TMEM_COLS = 512;            // two accumulators of 256 columns
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BAR_BYTES = 384;
 
 struct Bars {
-  uint64_t a_full[A_BUFS], a_empty[A_BUFS];
+  uint64_t a_full[MAX_AB], a_empty[MAX_AB];
   uint64_t w_full[MAX_WS], w_empty[MAX_WS];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
@@ -54,7 +55,7 @@ struct SlabParams {
   int c_chunks, row_tiles, npad, tma_out, img;
   int lo;             // smallest tap shift: the slab of tile rt starts at row rt * 128 + lo
   int RB;             // rows per TMA box (two boxes per slab)
-  int a_buf_bytes, w_slot_bytes, WS, off_w, off_epi, off_bar;
+  int a_buf_bytes, w_slot_bytes, AB, WS, off_w, off_epi, off_bar;   // AB slab buffers, WS weight stages
   int base_off;       // 1: descriptors carry the row phase in their base-offset field
   int64_t G;
 };
@@ -127,14 +128,13 @@ __device__ void slab_producer(const SlabParams& kp, const CUtensorMap* x_map, ui
   const Units<PAIR> units(kp);
   const uint32_t sm_base = smem_u32(sm);
   const uint32_t box_bytes = (uint32_t)kp.RB * 128u;
-  uint32_t n = 0;
+  uint32_t ab = 0, around = 0;
   for (int i = 0; i < units.count; ++i) {
     int ph, rt;
     units.at(i, ph, rt);
     const int row_start = rt * TILE_M + kp.lo;
-    for (int cc = 0; cc < kp.c_chunks; ++cc, ++n) {
-      const uint32_t ab = n & 1;
-      if (n >= A_BUFS) mbar_wait_idle(&bars->a_empty[ab], ((n >> 1) - 1) & 1);
+    for (int cc = 0; cc < kp.c_chunks; ++cc) {
+      if (around > 0) mbar_wait_idle(&bars->a_empty[ab], (around - 1) & 1);
       if (elect_one()) {
         const uint32_t dst = sm_base + ab * (uint32_t)kp.a_buf_bytes;
         mbar_arrive_expect_tx(&bars->a_full[ab], 2 * box_bytes);
@@ -142,6 +142,7 @@ __device__ void slab_producer(const SlabParams& kp, const CUtensorMap* x_map, ui
         tma_load_2d(dst + box_bytes, x_map, cc * 64, row_start + kp.RB, &bars->a_full[ab]);
       }
       __syncwarp();
+      if (++ab == (uint32_t)kp.AB) { ab = 0; ++around; }
     }
   }
 }
@@ -191,7 +192,7 @@ __device__ void mma_issuer(const SlabParams& kp, uint8_t* sm, Bars* bars, uint32
   const uint32_t sm_base = smem_u32(sm);
   const uint32_t idesc = make_idesc_bf16(PAIR ? 256u : 128u, (uint32_t)kp.npad);
   const Units<PAIR> units(kp);
-  uint32_t s = 0, wround = 0, na = 0, tcount = 0;
+  uint32_t s = 0, wround = 0, ab = 0, around = 0, tcount = 0;
   for (int i = 0; i < units.count; ++i, ++tcount) {
     int ph, rt;
     units.at(i, ph, rt);
@@ -199,9 +200,8 @@ __device__ void mma_issuer(const SlabParams& kp, uint8_t* sm, Bars* bars, uint32
     const uint32_t slot = tcount & 1;
     if (tcount >= 2) wait_full<PAIR>(&bars->acc_empty[slot], ((tcount >> 1) - 1) & 1);
     const uint32_t d = tmem_base + slot * 256;
-    for (int cc = 0; cc < kp.c_chunks; ++cc, ++na) {
-      const uint32_t ab = na & 1;
-      wait_full<PAIR>(&bars->a_full[ab], (na >> 1) & 1);
+    for (int cc = 0; cc < kp.c_chunks; ++cc) {
+      wait_full<PAIR>(&bars->a_full[ab], around & 1);
       const uint32_t a_lo0 = smem_desc_lo(sm_base + ab * (uint32_t)kp.a_buf_bytes);
       for (int t = 0; t < P.ntaps; ++t) {
         wait_full<PAIR>(&bars->w_full[s], wround & 1);
@@ -231,6 +231,7 @@ __device__ void mma_issuer(const SlabParams& kp, uint8_t* sm, Bars* bars, uint32
         __syncwarp();
         if (++s == (uint32_t)kp.WS) { s = 0; ++wround; }
       }
+      if (++ab == (uint32_t)kp.AB) { ab = 0; ++around; }
     }
   }
 }
@@ -242,14 +243,13 @@ __device__ void relay_peer(const SlabParams& kp, Bars* bars) {
   const uint32_t a_full_leader0 = mapa_rank(smem_u32(&bars->a_full[0]), 0);
   const uint32_t w_full_leader0 = mapa_rank(smem_u32(&bars->w_full[0]), 0);
   const Units<true> units(kp);
-  uint32_t s = 0, wround = 0, na = 0;
+  uint32_t s = 0, wround = 0, ab = 0, around = 0;
   for (int i = 0; i < units.count; ++i) {
     int ph, rt;
     units.at(i, ph, rt);
     const int ntaps = p.phase[ph].ntaps;
-    for (int cc = 0; cc < kp.c_chunks; ++cc, ++na) {
-      const uint32_t ab = na & 1;
-      mbar_wait(&bars->a_full[ab], (na >> 1) & 1);
+    for (int cc = 0; cc < kp.c_chunks; ++cc) {
+      mbar_wait(&bars->a_full[ab], around & 1);
       if (elect_one()) mbar_arrive_remote(a_full_leader0 + ab * 8);
       __syncwarp();
       for (int t = 0; t < ntaps; ++t) {
@@ -258,6 +258,7 @@ __device__ void relay_peer(const SlabParams& kp, Bars* bars) {
         __syncwarp();
         if (++s == (uint32_t)kp.WS) { s = 0; ++wround; }
       }
+      if (++ab == (uint32_t)kp.AB) { ab = 0; ++around; }
     }
   }
 }
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_slab_kernel(const __grid_con
   const bool leader = !PAIR || (blockIdx.x & 1) == 0;
   if (threadIdx.x == 0) {
     // pairs: the leader's "full" barriers also collect the peer's relay, its acc_empty both CTAs' epilogue warps
-    for (int a = 0; a < A_BUFS; ++a) {
+    for (int a = 0; a < MAX_AB; ++a) {
       mbar_init(&bars->a_full[a], PAIR && leader ? 2 : 1);
       mbar_init(&bars->a_empty[a], 1);
     }
@@ -468,16 +469,22 @@ extern "C" int cp_conv_slab(const cp_conv_slab_params* pp, cp_stream_t s) {
   kp.a_buf_bytes = 2 * kp.RB * 128;
   const int w_rows = pair ? kp.npad / 2 : kp.npad;
   kp.w_slot_bytes = (w_rows * 128 + 1023) / 1024 * 1024;
-  const int fixed = 1024 + A_BUFS * kp.a_buf_bytes + 4 * 2 * EPI_TILE_BYTES + 256;
-  kp.WS = (SMEM_LIMIT - fixed) / kp.w_slot_bytes;
+  // shared memory: 4 weight stages first, then as many slab buffers as fit (2..6: the narrow convolutions are bound by the
+  // activation stream and want it deep), the rest goes back to the weight ring
+  const int avail = SMEM_LIMIT - (1024 + 4 * 2 * EPI_TILE_BYTES + BAR_BYTES);
+  kp.AB = (avail - 4 * kp.w_slot_bytes) / kp.a_buf_bytes;
+  kp.AB = kp.AB > MAX_AB ? MAX_AB : kp.AB;
+  if (const char* ab_env = getenv("CP_SLAB_AB")) kp.AB = atoi(ab_env) < kp.AB && atoi(ab_env) >= 2 ? atoi(ab_env) : kp.AB;   // A/B measurements
+  CP_REQUIRE(kp.AB >= 2, CP_E_UNSUPPORTED, "cp_conv_slab: no room for two activation slabs");
+  kp.WS = (avail - kp.AB * kp.a_buf_bytes) / kp.w_slot_bytes;
   kp.WS = kp.WS > MAX_WS ? MAX_WS : kp.WS;
-  if (const char* ws_env = getenv("CP_SLAB_WS")) kp.WS = atoi(ws_env) < kp.WS && atoi(ws_env) >= 2 ? atoi(ws_env) : kp.WS;   // A/B measurements
+  if (const char* ws_env = getenv("CP_SLAB_WS")) kp.WS = atoi(ws_env) < kp.WS && atoi(ws_env) >= 2 ? atoi(ws_env) : kp.WS;
   CP_REQUIRE(kp.WS >= 2, CP_E_UNSUPPORTED, "cp_conv_slab: no room for the weight ring");
-  kp.off_w = A_BUFS * kp.a_buf_bytes;
+  kp.off_w = kp.AB * kp.a_buf_bytes;
   kp.off_epi = kp.off_w + kp.WS * kp.w_slot_bytes;
   kp.off_bar = kp.off_epi + 4 * 2 * EPI_TILE_BYTES;
-  const int smem = kp.off_bar + 256 + 1024;
-  static_assert(sizeof(Bars) <= 256, "barrier block");
+  const int smem = kp.off_bar + BAR_BYTES + 1024;
+  static_assert(sizeof(Bars) <= BAR_BYTES, "barrier block");
 
   CUtensorMap x_map, out_map;
   memset(&out_map, 0, sizeof(out_map));

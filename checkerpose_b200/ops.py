@@ -384,7 +384,8 @@ def conv_slab_same(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
             ph.shift[t] = (ky - KH // 2) * Wp + (kx - KW // 2)
     p.vy0, p.vy1, p.vx0, p.vx1 = 0, Hp - 1, 0, Wp - 1
     p.compact = 0
-    _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
+    # signature: ..., rows of the launch, multiply-accumulates of the convolution proper (without the border rows)
+    _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, B * (Hp - 1) * (Wp - 1) * KH * KW * Cin * int(nout)))
     return out
 
 
@@ -407,7 +408,7 @@ def conv_slab_full(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
             ph.shift[t] = (ky - 1) * Wp + (kx - 1)
     p.vy0, p.vy1, p.vx0, p.vx1 = 0, Hp, 0, Wp
     p.compact = 0
-    _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
+    _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, B * Hp * Wp * KH * KW * Cin * int(nout)))
     return out
 
 
@@ -440,7 +441,7 @@ def convT_slab(x_nhwc, w_packed, nout, bias=None, act=False, slope=0.0):
             ph.out_off = dy * OWp + dx
     p.vy0, p.vy1, p.vx0, p.vx1 = 0, H, 0, W
     p.compact, p.out_sb, p.out_sy, p.out_sx = 1, OHp * OWp, 2 * OWp, 2
-    _conv_slab(p, ("CS", 9 * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, 0))
+    _conv_slab(p, ("CS", 9 * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, B * H * W * 9 * Cin * int(nout)))
     return out
 
 

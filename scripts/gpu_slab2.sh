@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-KB_CHECK_ONLY=1 timeout 120 python scripts/kbench_slab.py 2>&1 | grep -v Warning
-echo "== pair"; KB_SHAPES=1 timeout 300 python scripts/kbench_slab.py 2>&1 | grep -E "^conv"
+( timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu --timeout 300 -p no:cacheprovider -k "slab or border" ) 2>&1 | grep -E "^E  |passed|failed|^FAILED" | head -20
+timeout 300 python scripts/kbench_slab.py 2>&1 | grep -E "^conv" | tee gpurun_out/kbench_slab.txt
+echo "== AB=2"; CP_SLAB_AB=2 timeout 300 python scripts/kbench_slab.py 2>&1 | grep -E "^conv"

@@ -8,7 +8,7 @@ import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print("ms/step", round(d["ms_per_step"], 3), "RoIs/s", round(d["value"]), "e2e", round(d["e2e"]["value"]),
       "K2 ms", round(d["roofline"]["avg_launch_ms"], 4), "frac", round(d["roofline"]["frac"], 3),
-      "K3 ms", round(d["roofline_k3"]["avg_launch_ms"], 4), "gnn_only", round(d["gnn_only"]["ms_per_step"],3), "parity", d["parity"]["keypoint_agreement"], d["clocks"], "launches", d["gpu_launches"])
+      "K3 ms", round(d["roofline_k3"]["avg_launch_ms"], 4), "gnn_only", round(d["gnn_only"]["ms_per_step"],3), "conv", (d.get("roofline_conv") or {}).get("ms_per_step"), (d.get("roofline_conv") or {}).get("achieved"), "parity", d["parity"]["keypoint_agreement"], d["clocks"], "launches", d["gpu_launches"])
 PY
 done
 tail -n 3 gpurun_out/bench.err

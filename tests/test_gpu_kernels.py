@@ -468,6 +468,31 @@ def test_conv_slab_matches_fp64(cp, monkeypatch, pair, kind, B, H, W, Cin, Cout)
     assert err < 6e-3, err
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("B,H,W,Ca,Cb,Cout,k", [(3, 8, 8, 128, 64, 256, 3), (2, 16, 16, 256, 256, 256, 3), (5, 5, 7, 64, 0, 64, 3), (2, 32, 32, 64, 64, 32, 1)])
+def test_conv_slab_fused_upsample_is_bit_identical(cp, monkeypatch, pair, B, H, W, Ca, Cb, Cout, k):
+    """The convolution whose loader warps interpolate the x2-upsampled, concatenated map on the fly must equal, bit for bit,
+    the same convolution over the map written by the stand-alone upsampling kernel (same bf16 activations, same MMA order)."""
+    ops = cp.ops
+    monkeypatch.setenv("CP_SLAB_PAIR", pair)
+    g = torch.Generator().manual_seed(B + H + Ca + Cout)
+    a = torch.randn(B, H, W, Ca, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2)
+    b = torch.randn(B, H, W, Cb, generator=g).to(torch.bfloat16).cuda().permute(0, 3, 1, 2) if Cb else None
+    if (Ca + Cb) % 64:
+        pytest.skip("channel count not a multiple of 64")
+    w = torch.randn(Cout, k * k * (Ca + Cb), generator=g) / (k * k * (Ca + Cb)) ** 0.5
+    bias = torch.randn(Cout, generator=g).cuda()
+    wp = ops.pack_weight(w.cuda())
+    two = ops.conv_slab_same(ops.upsample2x_cat_padded(a, b), wp, Cout, k, k, bias, True, 0.0)
+    one = ops.conv_slab_same_up(a, b, wp, Cout, k, k, bias, True, 0.0)
+    assert one.shape == two.shape == (B, 2 * H + 1, 2 * W + 1, Cout)
+    assert torch.equal(one, two)
+    # a strided source: the interior of a bordered map
+    buf = ops.to_bordered(a.permute(0, 2, 3, 1)).contiguous()
+    view = buf[:, :-1, :-1].permute(0, 3, 1, 2)
+    assert torch.equal(ops.conv_slab_same_up(view, b, wp, Cout, k, k, bias, True, 0.0), two)
+
+
 def test_zero_border_and_padded_upsample(cp):
     """cp_zero_border_nhwc + cp_upsample2x_cat_nhwc_to: the padded upsampling equals the plain one inside a zero border."""
     ops = cp.ops

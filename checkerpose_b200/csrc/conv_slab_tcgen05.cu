@@ -44,6 +44,8 @@ constexpr int EPI_TILE_BYTES = 32 * 64;   // 32 rows x 32 bf16 (SWIZZLE_64B) per
 constexpr int TMEM_COLS = 512;            // two accumulators of 256 columns
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 384;
+constexpr int SEG_MAX = 4;
+constexpr int SEG_BYTES = SEG_MAX * 256 * 4;    // fused 1x1 head: its weights (seg_n x Nout fp32), after the barrier block
 
 struct Bars {
   uint64_t a_full[MAX_AB], a_empty[MAX_AB];
@@ -384,6 +386,7 @@ __device__ void epilogue(const SlabParams& kp, const CUtensorMap* out_map, uint8
     while (!mbar_try_wait(&bars->acc_full[slot], (tcount >> 1) & 1)) __nanosleep(64);   // idle for a whole K loop: do not spin
     tc_fence_after_sync();
     const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
+    float seg_acc[SEG_MAX] = {0.f, 0.f, 0.f, 0.f};
     for (int n0 = 0; n0 < kp.npad; n0 += 32) {
       if (n0 >= p.Nout) break;
       uint32_t r[32];
@@ -406,6 +409,23 @@ __device__ void epilogue(const SlabParams& kp, const CUtensorMap* out_map, uint8
         float x0 = __uint_as_float(r[2 * e]) + bv[2 * e], x1 = __uint_as_float(r[2 * e + 1]) + bv[2 * e + 1];
         if (p.act) { x0 = cp::lrelu(x0, p.slope); x1 = cp::lrelu(x1, p.slope); }
         w[e] = valid ? f2_to_bf2(x0, x1) : 0u;      // outside the window the grid keeps its zero border
+      }
+      if (p.seg_w) {      // fused 1x1 head over the bf16 values this row stores
+        const float4* sw4 = reinterpret_cast<const float4*>(sm + kp.off_bar + BAR_BYTES);
+#pragma unroll
+        for (int j = 0; j < SEG_MAX; ++j) {
+          if (j >= p.seg_n) break;
+          float a = seg_acc[j];
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 c = sw4[j * 64 + (n0 >> 2) + e4];
+            a = fmaf(__uint_as_float(w[2 * e4] << 16), c.x, a);
+            a = fmaf(__uint_as_float(w[2 * e4] & 0xffff0000u), c.y, a);
+            a = fmaf(__uint_as_float(w[2 * e4 + 1] << 16), c.z, a);
+            a = fmaf(__uint_as_float(w[2 * e4 + 1] & 0xffff0000u), c.w, a);
+          }
+          seg_acc[j] = a;
+        }
       }
       if (kp.tma_out) {
         const uint32_t tbuf = tbuf0 + (nstore & 1) * EPI_TILE_BYTES;
@@ -439,6 +459,15 @@ __device__ void epilogue(const SlabParams& kp, const CUtensorMap* out_map, uint8
       if (PAIR) mbar_arrive_remote(acc_empty_leader0 + slot * 8);
       else mbar_arrive(&bars->acc_empty[slot]);
     }
+    if (p.seg_w && valid) {
+      const int Hs = p.vy1 - p.vy0, Ws = p.vx1 - p.vx0;
+      const int b = (int)(g / kp.img);
+      const int rem = (int)(g - (int64_t)b * kp.img);
+      const int py = rem / p.Wp, px = rem - py * p.Wp;
+#pragma unroll
+      for (int j = 0; j < SEG_MAX; ++j)
+        if (j < p.seg_n) p.seg_out[(((int64_t)b * p.seg_n + j) * Hs + (py - p.vy0)) * Ws + (px - p.vx0)] = seg_acc[j] + __ldg(p.seg_b + j);
+    }
   }
   if (kp.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
@@ -470,6 +499,13 @@ __global__ void __launch_bounds__(UP ? NTHREADS_UP : NTHREADS, 1) conv_slab_kern
   if (warp == 2) {
     if (PAIR) tmem_alloc_pair(&bars->tmem_slot, TMEM_COLS);
     else tmem_alloc(&bars->tmem_slot, TMEM_COLS);
+  }
+  if (kp.p.seg_w) {   // fused 1x1 head: weights zero-padded to npad columns
+    float* sw = reinterpret_cast<float*>(sm + kp.off_bar + BAR_BYTES);
+    for (int i = threadIdx.x; i < kp.p.seg_n * 256; i += blockDim.x) {
+      const int j = i >> 8, n = i & 255;
+      sw[i] = n < kp.p.Nout ? __ldg(kp.p.seg_w + (size_t)j * kp.p.Nout + n) : 0.f;
+    }
   }
   tc_fence_before_sync();
   if (PAIR) cluster_sync_all();     // both CTAs' barriers exist before anyone arrives remotely
@@ -538,6 +574,8 @@ extern "C" int cp_conv_slab(const cp_conv_slab_params* pp, cp_stream_t s) {
   CP_REQUIRE(p.num_phases >= 1 && p.num_phases <= CP_SLAB_MAX_PHASES && (p.num_phases == 1 || p.compact), CP_E_INVALID,
              "cp_conv_slab: %d phases (several phases need a compact destination)", p.num_phases);
   CP_REQUIRE(p.vy0 >= 0 && p.vy1 <= p.Hp && p.vx0 >= 0 && p.vx1 <= p.Wp && p.vy0 < p.vy1 && p.vx0 < p.vx1, CP_E_INVALID, "cp_conv_slab: bad output window");
+  CP_REQUIRE(!p.seg_w || (p.seg_b && p.seg_out && p.seg_n >= 1 && p.seg_n <= SEG_MAX && !p.compact && p.num_phases == 1), CP_E_INVALID,
+             "cp_conv_slab: the fused 1x1 head needs bias, output, 1..%d channels and a same-grid destination", SEG_MAX);
   SlabParams kp;
   memset(&kp, 0, sizeof(kp));
   kp.p = p;
@@ -577,7 +615,7 @@ extern "C" int cp_conv_slab(const cp_conv_slab_params* pp, cp_stream_t s) {
   kp.w_slot_bytes = (w_rows * 128 + 1023) / 1024 * 1024;
   // shared memory: 4 weight stages first, then as many slab buffers as fit (2..6: the narrow convolutions are bound by the
   // activation stream and want it deep), the rest goes back to the weight ring
-  const int avail = SMEM_LIMIT - (1024 + 4 * 2 * EPI_TILE_BYTES + BAR_BYTES);
+  const int avail = SMEM_LIMIT - (1024 + 4 * 2 * EPI_TILE_BYTES + BAR_BYTES + SEG_BYTES);
   kp.AB = (avail - 4 * kp.w_slot_bytes) / kp.a_buf_bytes;
   kp.AB = kp.AB > MAX_AB ? MAX_AB : kp.AB;
   if (const char* ab_env = getenv("CP_SLAB_AB")) kp.AB = atoi(ab_env) < kp.AB && atoi(ab_env) >= 2 ? atoi(ab_env) : kp.AB;   // A/B measurements
@@ -589,7 +627,7 @@ extern "C" int cp_conv_slab(const cp_conv_slab_params* pp, cp_stream_t s) {
   kp.off_w = kp.AB * kp.a_buf_bytes;
   kp.off_epi = kp.off_w + kp.WS * kp.w_slot_bytes;
   kp.off_bar = kp.off_epi + 4 * 2 * EPI_TILE_BYTES;
-  const int smem = kp.off_bar + BAR_BYTES + 1024;
+  const int smem = kp.off_bar + BAR_BYTES + SEG_BYTES + 1024;
   static_assert(sizeof(Bars) <= BAR_BYTES, "barrier block");
 
   CUtensorMap x_map, out_map;

@@ -569,9 +569,12 @@ class _SlabConvSeq(_OwnConvSeq):
     def _pad_channels(buf, cin_pad):
         return buf if buf.shape[-1] == cin_pad else F.pad(buf, (0, cin_pad - buf.shape[-1]))
 
-    def __call__(self, x, skip=None):
+    def __call__(self, x, skip=None, seg=None):
+        """``seg`` = (weight (n, C), bias (n,)) f32 of a 1x1 convolution to fuse into this block's LAST convolution: the
+        result gains the attribute ``_cp_seg`` = its (B, n, H, W) f32 output (None when the shapes do not allow the fusion)."""
         kinds = self.ops
         start = 0
+        seg_out = None
         buf = None          # zero-bordered (B,H+2,W+2,C) map, or None while y (plain NHWC) holds the current map
         y = None
         if kinds[0][0] == "up":
@@ -599,7 +602,8 @@ class _SlabConvSeq(_OwnConvSeq):
                 if skip is not None:
                     x = torch.cat([x, skip], dim=1)
                 y = self._nhwc(x)
-        for kind, ws, b, geom, relu in kinds[start:]:
+        for oi in range(start, len(kinds)):
+            kind, ws, b, geom, relu = kinds[oi]
             if kind == "relu":
                 cur = buf if buf is not None else y
                 torch.relu_(cur)
@@ -616,7 +620,10 @@ class _SlabConvSeq(_OwnConvSeq):
                     buf, y = ops.to_bordered(y), None
                 buf = self._pad_channels(buf, cin_pad)
                 if same:
-                    buf = ops.conv_slab_same(buf, ws, cout, kh, kw, b, relu, 0.0)
+                    if seg is not None and oi == len(kinds) - 1 and seg[0].shape[1] == cout:
+                        buf, seg_out = ops.conv_slab_same(buf, ws, cout, kh, kw, b, relu, 0.0, seg=seg)
+                    else:
+                        buf = ops.conv_slab_same(buf, ws, cout, kh, kw, b, relu, 0.0)
                 else:
                     y, buf = ops.conv_slab_full(buf, ws, cout, kh, kw, b, relu, 0.0), None
                 continue
@@ -630,7 +637,9 @@ class _SlabConvSeq(_OwnConvSeq):
             else:
                 Ho, Wo = (H - 1) * 2 - 2 * pad + kh + 1, (W - 1) * 2 - 2 * pad + kw + 1
             y = ops.conv_bf16(y, ws, cout, kh, kw, pad, Ho, Wo, b, relu, 0.0, transposed=(kind == "convT"))
-        return self._view(buf) if buf is not None else y.permute(0, 3, 1, 2)
+        res = self._view(buf) if buf is not None else y.permute(0, 3, 1, 2)
+        res._cp_seg = seg_out
+        return res
 
 
 def _x3_module(module):
@@ -684,15 +693,26 @@ def reuse_image_branch():
         _IMG_REUSE = None
 
 
-def image_block(module, x, dtype, skip=None):
+def _seg_weights(seg_module):
+    """(weight (n, C) f32, bias (n,) f32) of a 1x1 seg_block that the slab convolution can fuse, else None."""
+    m = seg_module
+    if not (isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1) and m.stride == (1, 1) and m.padding == (0, 0) and m.groups == 1
+            and m.bias is not None and m.out_channels <= 4):
+        return None
+    return _PREP.get(m, ("segw",), lambda: (m.weight.detach().float().reshape(m.out_channels, -1).contiguous(), m.bias.detach().float().contiguous()))
+
+
+def image_block(module, x, dtype, skip=None, seg_module=None):
     """Run an image-branch block (up_net[i], patch_generator, seg_block) in ``dtype``; ``skip`` is concatenated
-    to ``x`` along the channels first (pipeline.py:372)."""
+    to ``x`` along the channels first (pipeline.py:372).  ``seg_module``: the 1x1 seg_block that will be applied to this
+    block's result -- the slab image branch computes it in the block's last epilogue (result attribute ``_cp_seg``)."""
     if _IMG_REUSE is not None and id(module) in _IMG_REUSE:
         return _IMG_REUSE[id(module)]
     if dtype == torch.bfloat16 and _IMAGE_BRANCH == "cudnn":
         y = _bf16_module(module)(x.to(torch.bfloat16), None if skip is None else skip.to(torch.bfloat16))
     elif dtype == torch.bfloat16:
-        y = _tc_module(module)(x, skip)
+        seq = _tc_module(module)
+        y = seq(x, skip, seg=_seg_weights(seg_module)) if seg_module is not None else seq(x, skip)
     else:
         y = _x3_module(module)(x.float(), None if skip is None else skip.float())
     if _IMG_REUSE is not None:
@@ -914,7 +934,8 @@ def pose_head_forward(net, img_feats, obj_ids=None, stage=None, dtype=None, bbox
     ops.decode_init(logits0, L0, Ltot, roi_bit, x_bits, y_bits, roi_mask, x_id, y_id, perm, sel)
     img_feat = feat_last
     for i in range(nact):
-        img_feat = image_block(net.up_net[i], img_feat, dtype, skip=img_feats[-i - 1] if i > 0 else None)
+        img_feat = image_block(net.up_net[i], img_feat, dtype, skip=img_feats[-i - 1] if i > 0 else None,
+                               seg_module=net.seg_block if i == nact - 1 else None)
         ctx = _stage_ctx(net, net.refine_net[i], obj_ids, B, dev, ctx0)
         last_kp = perm is not None and i == nact - 1     # last stage: the ids the caller sees, in keypoint order
         x_kp, y_kp = (torch.empty_like(x_id), torch.empty_like(y_id)) if last_kp else (None, None)
@@ -927,7 +948,9 @@ def pose_head_forward(net, img_feats, obj_ids=None, stage=None, dtype=None, bbox
     if perm is not None and nact == 0:
         x_id = ops.permute_rows(x_id.view(B, N, 1), perm, sel, True).view(B, N)
         y_id = ops.permute_rows(y_id.view(B, N, 1), perm, sel, True).view(B, N)
-    seg = image_block(net.seg_block, img_feat, dtype).float().contiguous()
+    seg = getattr(img_feat, "_cp_seg", None)         # fused into the last up_net convolution's epilogue (slab image branch)
+    if seg is None:
+        seg = image_block(net.seg_block, img_feat, dtype).float().contiguous()
     corr = None
     if bbox is not None:
         corr = (ops.correspondences_packed if packed else ops.correspondences)(roi_bit, seg, bbox, x_id, y_id)

@@ -365,13 +365,27 @@ def to_bordered(x_nhwc):
     return torch.nn.functional.pad(x_nhwc, (0, 0, 0, 1, 0, 1))
 
 
-def conv_slab_same(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
+def _slab_seg(p, seg, B, Hp, Wp, nout, dev):
+    """Attach the fused 1x1 head (seg = (weight (n, nout) f32, bias (n,) f32)) -> its (B, n, H, W) f32 output."""
+    if seg is None:
+        return None
+    sw, sb = seg
+    _need_cuda(sw, sb)
+    assert sw.dtype == torch.float32 and sb.dtype == torch.float32 and sw.is_contiguous() and sw.shape == (sb.shape[0], nout) and sw.shape[0] <= 4
+    seg_out = torch.empty((B, sw.shape[0], Hp - 1, Wp - 1), dtype=torch.float32, device=dev)
+    p.seg_w, p.seg_b, p.seg_out, p.seg_n = _p(sw), _p(sb), _p(seg_out), int(sw.shape[0])
+    return seg_out
+
+
+def conv_slab_same(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0, seg=None):
     """Conv2d KH x KW (1 or 3), stride 1, "same" padding, over a bordered bf16 map xp (B, H+1, W+1, Cin) -> the bordered
     (B, H+1, W+1, nout) map of the result (its border written as zeros): chains of such convolutions never leave the
-    layout.  W rows in (ky, kx, c) order, packed by pack_weight."""
+    layout.  W rows in (ky, kx, c) order, packed by pack_weight.  seg = (weight (n, nout), bias (n,)) f32 fuses a 1x1
+    convolution of the result (seg_block) into the epilogue: returns (map, (B, n, H, W) f32)."""
     B, Hp, Wp, Cin = xp.shape
     assert KH % 2 == 1 and KW % 2 == 1 and KH <= 3 and KW <= 3
     p = _slab_common(xp, w_packed, KH * KW * Cin, nout, bias, act, slope)
+    seg_out = _slab_seg(p, seg, B, Hp, Wp, nout, xp.device)
     out = torch.empty((B, Hp, Wp, nout), dtype=torch.bfloat16, device=xp.device)
     p.out, p.ld_out = _p(out), int(nout)
     p.num_phases = 1
@@ -386,7 +400,7 @@ def conv_slab_same(xp, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):
     p.compact = 0
     # signature: ..., rows of the launch, multiply-accumulates of the convolution proper (without the border rows)
     _conv_slab(p, ("CS", KH * KW * Cin, (int(nout),), OUT_BF16, B * Hp * Wp, B * (Hp - 1) * (Wp - 1) * KH * KW * Cin * int(nout)))
-    return out
+    return out if seg is None else (out, seg_out)
 
 
 def conv_slab_same_up(a, b, w_packed, nout, KH, KW, bias=None, act=False, slope=0.0):

@@ -177,6 +177,10 @@ typedef struct {
   const void* up_a; int64_t up_a_sb, up_a_sh, up_a_sw; int up_Ca;
   const void* up_b; int64_t up_b_sb, up_b_sh, up_b_sw; int up_Cb;
   int up_H, up_W;
+  /* Fused 1x1 head on the convolution's own output (seg_w != NULL; needs compact == 0): seg_block of pipeline.py:349,383.
+   * seg_out[b, j, py - vy0, px - vx0] = seg_b[j] + sum_n bf16(out[g, n]) * seg_w[j, n]  (fp32, NCHW (B, seg_n, vy1-vy0, vx1-vx0)),
+   * computed in the epilogue from the values being stored: the map is not read again.  seg_n <= 4. */
+  const float* seg_w; const float* seg_b; float* seg_out; int seg_n;
 } cp_conv_slab_params;
 int cp_conv_slab(const cp_conv_slab_params* p, cp_stream_t s);
 /* zero the border of a bordered NHWC map (B, Hp, Wp, C) of elem_bytes-wide elements (row pitch C): the LAST row and the LAST

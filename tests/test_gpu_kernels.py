@@ -493,6 +493,28 @@ def test_conv_slab_fused_upsample_is_bit_identical(cp, monkeypatch, pair, B, H, 
     assert torch.equal(ops.conv_slab_same_up(view, b, wp, Cout, k, k, bias, True, 0.0), two)
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,nseg", [(3, 16, 16, 128, 256, 2), (2, 9, 11, 64, 64, 1), (2, 12, 12, 64, 256, 4)])
+def test_conv_slab_fused_seg_head(cp, monkeypatch, pair, B, H, W, Cin, Cout, nseg):
+    """seg_block (1x1) computed in the last convolution's epilogue: equals the 1x1 convolution of the bf16 map the same launch
+    stores (float64 reference on exactly those values), and the map itself is unchanged by the fusion."""
+    ops = cp.ops
+    monkeypatch.setenv("CP_SLAB_PAIR", pair)
+    g = torch.Generator().manual_seed(B + H + Cout + nseg)
+    xp = ops.to_bordered(torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16).cuda()).contiguous()
+    wp = ops.pack_weight((torch.randn(Cout, 9 * Cin, generator=g) / (9 * Cin) ** 0.5).cuda())
+    bias = torch.randn(Cout, generator=g).cuda()
+    sw = (torch.randn(nseg, Cout, generator=g) / Cout ** 0.5).cuda()
+    sb = torch.randn(nseg, generator=g).cuda()
+    plain = ops.conv_slab_same(xp, wp, Cout, 3, 3, bias, True, 0.0)
+    out, seg = ops.conv_slab_same(xp, wp, Cout, 3, 3, bias, True, 0.0, seg=(sw, sb))
+    assert torch.equal(out, plain) and seg.shape == (B, nseg, H, W) and seg.dtype == torch.float32
+    ref = torch.einsum("bhwc,jc->bjhw", out[:, :-1, :-1].double(), sw.double()) + sb.double().view(1, -1, 1, 1)
+    err = float((seg.double() - ref).abs().max() / ref.abs().max())
+    print(f"fused seg pair={pair}: max err / max = {err:.2e}")
+    assert err < 1e-5, err
+
+
 def test_zero_border_and_padded_upsample(cp):
     """cp_zero_border_nhwc + cp_upsample2x_cat_nhwc_to: the padded upsampling equals the plain one inside a zero border."""
     ops = cp.ops

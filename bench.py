@@ -525,7 +525,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": wl["text"], "name": wl["name"], "rois_per_gpu": B, "rois_total": B * world, "npoint": N, "graph_k": case["K"],
                        "objects": f"{wl['ds']}/{wl['objs'][0]}" if len(wl["objs"]) == 1 else f"{wl['ds']}: {len(wl['objs'])} graphs, selected per RoI",
-                       "image_branch": ("included: our implicit-GEMM convolutions on tcgen05 (cp_conv_bf16 / cp_gemm_x3), no library kernel"
+                       "image_branch": ("included: our implicit-GEMM convolutions on tcgen05 (cp_conv_slab / cp_conv_bf16 / cp_gemm_x3), no library kernel"
                                         if (args.image_branch == "tcgen05" or args.dtype == "fp32") else "included (cuDNN, library part of the path)"),
                        "inputs": ("the 1024@8^2 HRNet map (all the init net reads, init.py:111-112)" if wl["init_only"] else
                                   "the three HRNet maps the head reads (256@32^2, 512@16^2, 1024@8^2); the 128@64^2 map is never read "
@@ -594,7 +594,7 @@ def main():
     ap.add_argument("--sweep-n", default="512,1024,2048,4096")
     ap.add_argument("--sweep-k", default="8,16,20,32,40")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--image-branch", default="cudnn", choices=["tcgen05", "cudnn"], help="bf16 mode: whose convolutions run the image branch")
+    ap.add_argument("--image-branch", default="tcgen05", choices=["tcgen05", "cudnn"], help="bf16 mode: whose convolutions run the image branch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: timed loop only, warm-up exactly --warmup")

@@ -652,15 +652,15 @@ def _tc_module(module):
     return _PREP.get(module, ("tcseq",), lambda: _SlabConvSeq(module))
 
 
-_IMAGE_BRANCH = "cudnn"
+_IMAGE_BRANCH = "tcgen05"
 
 
 def set_image_branch(kind: str) -> None:
-    """bf16 mode only: "tcgen05" = the image branch on cp_conv_bf16 (our implicit-GEMM kernel: 1.3-1.45 PFLOP/s on the 3x3
-    convolutions, no library kernel anywhere in the head), "cudnn" = the library convolutions (SURVEY 8a marks them as the
-    library part of the path).  Measured end to end: 15.2 vs 14.05 ms per step -- cuDNN's sm_100 kernels
-    are ahead on the two 64 x 64 convolutions, the transposed convolution and the narrow outputs -- so "cudnn" is the default
-    and "tcgen05" the switch for a head without library kernels.  The float32 mode never uses a library kernel."""
+    """bf16 mode only: "tcgen05" (default) = the image branch on our slab convolutions (cp_conv_slab; cp_conv_bf16 for conv1x1:
+    no library kernel anywhere in the head), "cudnn" = the library convolutions through torch (SURVEY 8a marks them as the
+    library part of the path; kept as the A/B arm).  Measured end to end: within about 1 % of each other
+    inside the power-capped step (14.55 vs 14.46 ms, 13.87 vs 13.87 ms on two boxes), with our kernels ahead on every
+    convolution in isolation.  The float32 mode never uses a library kernel."""
     global _IMAGE_BRANCH
     if kind not in ("tcgen05", "cudnn"):
         raise ValueError("image branch must be 'tcgen05' or 'cudnn'")

@@ -596,7 +596,7 @@ def test_bf16_image_branch_on_tcgen05_matches_the_library_branch(golden, name):
             outs[kind] = run_net(net, feats, p3d, obj_ids, lm)
     finally:
         head.set_compute_dtype(torch.float32)
-        head.set_image_branch("cudnn")
+        head.set_image_branch("tcgen05")
     for kind, (roi, xb, yb, seg, xid, yid) in outs.items():
         for a, ref in ((roi, g["roi_bit"]), (xb[:, :3], g["x_bits"][:, :3]), (yb[:, :3], g["y_bits"][:, :3])):
             d = a.cpu().numpy() - ref

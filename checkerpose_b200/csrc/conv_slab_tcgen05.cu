@@ -5,12 +5,15 @@
 // cp_conv_bf16 (conv_bf16_tcgen05.cu) gathers the rows of every kernel tap again -- 9 x 16 KB of cp.async traffic and
 // shared-memory writes per 64-channel slice of a 3 x 3 convolution, next to 9 x 32 KB of weights: with operand reads on top the
 // shared-memory port, not the tensor pipe, sets its pace (64 % of the MMA rate).  Here the map carries its own zero border,
+// (an image (H, W) is stored as (H+1, W+1) with a zero last row and column: over the flat index these are all four borders),
 // so over the flat pixel index g = (b * Hp + py) * Wp + px a tap is a constant row shift:
 //   out[g] = act(sum_t x[g + shift_t, :] . W_t^T + bias)
 // and a tile of 128 consecutive positions needs ONE slab of 128 + max shift - min shift rows per channel slice (262 rows for
 // 3 x 3 on a 64 x 64 map: 34 KB instead of 144 KB).  The slab is loaded by two TMA tensor copies (SWIZZLE_128B; rows before /
 // after the matrix zero-filled), and tap t is the same shared memory read through a descriptor whose start address is moved
-// by shift_t rows -- the row phase (shift & 7) goes into the descriptor's base-offset field.  No loader warps at all.
+// by shift_t rows.  Measured on B200: tcgen05.mma applies the 128-byte swizzle on ABSOLUTE shared-memory address bits (the
+// pattern TMA wrote), so a start address that is not a multiple of 8 rows needs nothing else -- putting the row phase into
+// the descriptor's base-offset field (bits 49-51) gives wrong results (CP_SLAB_BASEOFF=1 reproduces that).  No loader warps.
 //
 // CTA pairs (cluster of 2, tcgen05.mma.cta_group::2, M = 256): each CTA holds the slab of its own 128 positions and HALF of
 // every weight tile; the leader's MMA reads both halves.  Weight traffic into each SM's shared memory halves again.

@@ -32,14 +32,21 @@ using namespace sm100;
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_G_WARPS = 4, G_THREADS = NUM_G_WARPS * 32;
+#ifndef CP_K3_GWARPS
+#define CP_K3_GWARPS 4
+#endif
 #ifndef CP_K3_EWARPS
 #define CP_K3_EWARPS 8
 #endif
-constexpr int E_WARP0 = 4, NUM_E_WARPS = CP_K3_EWARPS;      // a multiple of 4: NUM_E_WARPS / 4 warps per TMEM lane quarter
-constexpr int W_WARP = E_WARP0 + NUM_E_WARPS, MMA_WARP = W_WARP + 1;
-constexpr int NUM_WARPS = NUM_E_WARPS == 8 ? 16 : MMA_WARP + 1;   // 8 epilogue warps: two idle warps, 512 threads leave 128 registers per thread
-static_assert(NUM_E_WARPS % 4 == 0 && E_WARP0 % 4 == 0, "epilogue warp w drains TMEM lane quarter w % 4");
+constexpr int NUM_G_WARPS = CP_K3_GWARPS, G_THREADS = NUM_G_WARPS * 32;
+constexpr int NUM_E_WARPS = CP_K3_EWARPS;      // a multiple of 4: NUM_E_WARPS / 4 warps per TMEM lane quarter
+// warp layout: gather warps first; with two gather warps the weight producer and the MMA issuer take warps 2 and 3 and
+// TWELVE epilogue warps fill 4..15 (the epilogue is what this kernel waits for); otherwise they follow the epilogue warps
+constexpr bool COMPACT_ROLES = NUM_G_WARPS == 2;
+constexpr int E_WARP0 = 4;
+constexpr int W_WARP = COMPACT_ROLES ? 2 : E_WARP0 + NUM_E_WARPS, MMA_WARP = W_WARP + 1;
+constexpr int NUM_WARPS = COMPACT_ROLES ? E_WARP0 + NUM_E_WARPS : (NUM_E_WARPS == 8 ? 16 : MMA_WARP + 1);   // 8 epilogue warps: two idle warps, 512 threads leave 128 registers per thread
+static_assert(NUM_E_WARPS % 4 == 0 && E_WARP0 % 4 == 0 && NUM_G_WARPS <= E_WARP0 && TILE_M % (NUM_G_WARPS * 4) == 0, "epilogue warp w drains TMEM lane quarter w % 4");
 constexpr int NTHREADS = NUM_WARPS * 32;
 constexpr int CHUNK_BYTES = TILE_M * 128;   // 128 rows x 64 bf16
 #ifndef CP_K3_NX
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) taps_chain_kernel(const __grid_co
 
   if (warp < NUM_G_WARPS) {
     gather_warps(kp, sm, bars, warp, lane);
-  } else if (warp < E_WARP0 + NUM_E_WARPS) {
+  } else if (warp >= E_WARP0 && warp < E_WARP0 + NUM_E_WARPS) {
     epilogue_warps(kp, &out_map, sm, bars, tmem_base, warp - E_WARP0, lane);
   } else if (warp == W_WARP) {
     weight_producer(kp, sm, bars);     // whole warp, warp-uniform control flow; an elected lane issues

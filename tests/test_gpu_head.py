@@ -607,3 +607,51 @@ def test_bf16_image_branch_on_tcgen05_matches_the_library_branch(golden, name):
         assert frac > 0.70
     a, b = outs["cudnn"], outs["tcgen05"]
     assert float((a[3] - b[3]).abs().max() / a[3].abs().max()) < 2e-2          # seg: two bf16 conv stacks with different summation orders
+
+
+def test_image_branch_blocks_vs_oracle():
+    """SURVEY 8f rank 1, block by block: every image-branch block of the bf16 mode on our own kernels -- up_net[0] (transposed
+    convolution as four parities + two 3x3), up_net[1] / up_net[2] (x2 bilinear upsampling of the concatenated skip + two 3x3),
+    patch_generator (2x2, padding 1) and seg_block (1x1, fused into the last up_net epilogue) -- against the oracle's fp32
+    restatement (oracle.upsample_module = get_gdrn_upsample_module pipeline.py:183-211; F.conv2d for :144-145 / :383) on the
+    same inputs, each block fed with the ORACLE's previous output.  Bar: 1e-2 of the block's output scale (bf16 operands and
+    stores, fp32 accumulation)."""
+    import torch.nn.functional as F
+    from checkerpose_b200 import head
+    from oracle import checkerpose_oracle as orc
+    name = "head_lmo_ape_n512_b1"
+    ds, objs, N, B, seed, lm = HEAD_CASES[name]
+    p3d, sd, feats, obj_ids = head_case_inputs(name)
+    net = build_net(N, p3d, lm, sd)
+    g = torch.Generator().manual_seed(99)
+    feats = syn.synthetic_features(3, g)                       # three RoIs: tiles that straddle images
+    assert head.get_image_branch() == "tcgen05"
+    x_ref = feats[-1]
+    seg_w, seg_b = sd["seg_block.weight"], sd["seg_block.bias"]
+    worst = 0.0
+    for i in range(3):
+        skip = feats[-i - 1] if i > 0 else None
+        xin = x_ref if skip is None else torch.cat([x_ref, skip], dim=1)
+        y_ref = orc.upsample_module(xin, sd, f"up_net.{i}.", is_convtrans=(i == 0))
+        y = head.image_block(net.up_net[i], x_ref.cuda(), torch.bfloat16, skip=None if skip is None else skip.cuda(),
+                             seg_module=net.seg_block if i == 2 else None)
+        assert y.shape == y_ref.shape and y.dtype == torch.bfloat16
+        e = float((y.float().cpu() - y_ref).abs().max() / y_ref.abs().max())
+        # patch_generator on OUR block output (picks up the bordered buffer), reference on the oracle's
+        pg = net.refine_net[i].local_feat_ext_block.patch_generator
+        p_ref = F.conv2d(y_ref, pg.weight.detach().cpu().float(), pg.bias.detach().cpu().float(), padding=pg.kernel_size[0] - 1)
+        pt = head.image_block(pg, y, torch.bfloat16)
+        ep = float((pt.float().cpu() - p_ref).abs().max() / p_ref.abs().max())
+        print(f"[image branch vs oracle] up_net[{i}] {tuple(y.shape)}: {e:.2e}   patch_generator {tuple(pt.shape)}: {ep:.2e}")
+        assert pt.shape == p_ref.shape and e < 1e-2 and ep < 1e-2, (i, e, ep)
+        worst = max(worst, e, ep)
+        if i == 2:
+            s_ref = F.conv2d(y_ref, seg_w, seg_b)
+            seg = getattr(y, "_cp_seg", None)
+            assert seg is not None and seg.shape == s_ref.shape and seg.dtype == torch.float32, "seg_block must come out of the fused epilogue"
+            es = float((seg.cpu() - s_ref).abs().max() / s_ref.abs().max())
+            unf = head.image_block(net.seg_block, y, torch.bfloat16).float().cpu()        # the unfused 1x1 on the same map
+            eu = float((unf - s_ref).abs().max() / s_ref.abs().max())
+            print(f"[image branch vs oracle] seg_block fused {es:.2e}, stand-alone {eu:.2e}")
+            assert es < 1e-2 and eu < 1.5e-2
+        x_ref = y_ref

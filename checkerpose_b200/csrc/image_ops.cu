@@ -58,7 +58,6 @@ template <> struct Vec<bf16> {
 // h0*(w0*a + w1*b) + h1*(w0*c + w1*d), then rounded to the output type), bf16 pairs are widened with one shift / one mask.
 template <typename T> struct Wide;
 template <> struct Wide<float> {
-  static constexpr int N = 4;
   using Raw = float4;
   __device__ static Raw load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
   __device__ static void fma(float (&o)[4], float w, const Raw& v, bool first) {
@@ -67,7 +66,6 @@ template <> struct Wide<float> {
   }
 };
 template <> struct Wide<bf16> {
-  static constexpr int N = 8;
   using Raw = uint4;
   __device__ static Raw load(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
   __device__ static void fma(float (&o)[8], float w, const Raw& v, bool first) {

@@ -310,7 +310,7 @@ pnp_ransac_kernel(const uint8_t* __restrict__ packed, const cp_corr_record* __re
   uint16_t* src = reinterpret_cast<uint16_t*>(xs + (size_t)N * 2);   // (N) keypoint id of the compacted entry
   uint8_t* mask = reinterpret_cast<uint8_t*>(src + N);        // (N) inlier flags of the compacted entries
   __shared__ double red[27 + (NT / 32) * 27];
-  __shared__ int warp_cnt[NT / 32], s_M, s_best_cnt, s_best_h;
+  __shared__ int warp_cnt[NT / 32], s_best_cnt, s_best_h;
   __shared__ Pose s_pose;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // records: packed rows (bbox + u16 per keypoint) or the 12-byte {u, v, flags} records of cp_correspondences

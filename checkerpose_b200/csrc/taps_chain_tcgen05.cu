@@ -58,7 +58,11 @@ constexpr int CHUNK_BYTES = TILE_M * 128;   // 128 rows x 64 bf16
 constexpr int NX = CP_K3_NX;                // gather ring slots
 constexpr int NH = 4;                       // chunks of h0 / h1 (256 channels)
 constexpr int B_STAGES = CP_K3_BSTAGES, B_STAGE_BYTES = 128 * 128;
-constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: a tile of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores
+constexpr int TBUF_BYTES = 32 * 64;          // per epilogue warp: tiles of 32 rows x 32 bf16 (SWIZZLE_64B) for the TMA stores
+#ifndef CP_K3_TBUFS
+#define CP_K3_TBUFS 1
+#endif
+constexpr int TBUFS = CP_K3_TBUFS;           // tiles per warp: with 2 a store only waits for the one before the previous
 constexpr int BIAS_FLOATS = 1024;           // 256 + 256 + 512
 constexpr int ACC_COLS = 256;
 constexpr int MAX_WT = 48;
@@ -67,7 +71,7 @@ constexpr int OFF_X = 0;
 constexpr int OFF_H = OFF_X + NX * CHUNK_BYTES;
 constexpr int OFF_B = OFF_H + NH * CHUNK_BYTES;
 constexpr int OFF_TBUF = OFF_B + B_STAGES * B_STAGE_BYTES;
-constexpr int OFF_BIAS = OFF_TBUF + NUM_E_WARPS * TBUF_BYTES;
+constexpr int OFF_BIAS = OFF_TBUF + NUM_E_WARPS * TBUFS * TBUF_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_FLOATS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 512;
 static_assert(SMEM_BYTES + 1024 <= 227 * 1024, "shared memory budget");
@@ -299,6 +303,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sm
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 __device__ void epilogue_warps(const TcParams& kp, const CUtensorMap* out_map, uint8_t* sm, Bars* bars, uint32_t tmem_base, int ew, int lane) {
   const cp_chain_params& p = kp.p;
@@ -306,7 +312,8 @@ __device__ void epilogue_warps(const TcParams& kp, const CUtensorMap* out_map, u
   const int row = q * 32 + lane;
   const uint32_t sm_base = smem_u32(sm);
   const uint32_t bias_s = sm_base + OFF_BIAS;
-  const uint32_t tbuf = sm_base + OFF_TBUF + ew * TBUF_BYTES;
+  const uint32_t tbuf0 = sm_base + OFF_TBUF + ew * (TBUFS * TBUF_BYTES);
+  uint32_t nstore = 0;
   const int sw = (lane >> 1) & 3;   // SWIZZLE_64B: 16-byte chunk index ^= bits 1-2 of the row
   uint32_t st = 0, hfree = 0;
   for (int tile = blockIdx.x; tile < kp.num_tiles; tile += gridDim.x) {
@@ -366,7 +373,9 @@ __device__ void epilogue_warps(const TcParams& kp, const CUtensorMap* out_map, u
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->h_full[c0 >> 6]);   // this warp's half of chunk c0 / 64 is in place
         } else {
-          if (lane == 0) bulk_wait_read0();   // the previous store is done reading the tile
+          const uint32_t tbuf = tbuf0 + (nstore % TBUFS) * TBUF_BYTES;
+          ++nstore;
+          if (lane == 0) bulk_wait_read_n<TBUFS - 1>();   // the store that last used this buffer is done reading it
           __syncwarp();
 #pragma unroll
           for (int e = 0; e < 4; ++e) sts128(tbuf + lane * 64 + ((e ^ sw) << 4), w[e]);
